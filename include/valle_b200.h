@@ -1,0 +1,216 @@
+/*
+ * valle_b200.h -- C ABI of libvalle_b200.so: the sm_100a (B200) VALL-E decoding engine.
+ *
+ * Drop-in boundary.  Every entry point takes raw device pointers,
+ * explicit sizes and a cudaStream_t (passed as void*); there are no torch / C++ types in any
+ * signature and no C++ exception crosses the ABI.  Return value: 0 = ok, non-zero = error
+ * code (message through vb_last_error(), thread-local).  OWNERSHIP: every buffer (weights,
+ * KV cache, workspaces, outputs) is allocated and freed by the caller (PyTorch on the Python
+ * side); the library allocates no persistent device memory and keeps no pointer past a call,
+ * except inside the explicit opaque `vb_decoder_t` handle (created / destroyed in pairs),
+ * which only stores the caller's pointers.
+ *
+ * Each function cites the reference interface (lifeiteng/vall-e, file:line under
+ * /root/reference) whose arithmetic it replaces.  Host-side callers mirror the reference's
+ * Python classes (valle_b200/modules, valle_b200/models); INTEGRATION.md shows the ctypes
+ * stub a reference maintainer would add.
+ */
+#ifndef VALLE_B200_H_
+#define VALLE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_ABI_VERSION 1
+
+enum vb_status { VB_OK = 0, VB_ERR_ARG = 1, VB_ERR_CUDA = 2, VB_ERR_UNSUPPORTED = 3 };
+/* storage type of the big matrices / activations.  Accumulation is always fp32. */
+enum vb_dtype { VB_F32 = 0, VB_BF16 = 1 };
+enum vb_epilogue { VB_EPI_NONE = 0, VB_EPI_RELU = 1, VB_EPI_RESIDUAL = 2 };
+/* attention visibility rule */
+enum vb_mask_mode {
+  VB_MASK_FULL = 0,    /* NAR: every row of a sequence sees the whole sequence (valle.py:1125-1127) */
+  VB_MASK_VALLE_AR = 1 /* AR: text rows see all text, audio rows see text + causal audio
+                          (valle.py:1010-1033): kv_len(i) = max(S, i + 1) */
+};
+
+typedef void *vb_stream_t; /* cudaStream_t */
+
+int vb_abi_version(void);
+const char *vb_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
+int64_t vb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a10  TokenEmbedding (valle/modules/embedding.py:21-47) and the 8-codebook sum composed by the
+ *      caller (valle/models/valle.py:1064,1110-1113,1134).
+ *   out[r,:] (=|+=) sum_{j<n_tables} tables[j][ tokens[r*tok_row_stride + j*tok_tab_stride] , :]
+ *   summed in table order j = 0..n_tables-1 (same association order as the reference).
+ *   tables: HOST array of n_tables device pointers to fp32 [vocab_j, d].
+ *   out_rows: NULL or device int32 [n_rows] destination row of each input row (ragged packing).
+ *   accumulate = 0: out = sum ; 1: out += sum
+ * ---------------------------------------------------------------------------------------- */
+int vb_embed_sum(const int64_t *tokens, int64_t tok_row_stride, int64_t tok_tab_stride,
+                 const float *const *tables, int n_tables, int64_t n_rows, int d, float *out,
+                 int64_t out_row_stride, const int32_t *out_rows, int accumulate, vb_stream_t stream);
+
+/* a11  SinePositionalEmbedding.forward (embedding.py:93-97, scale=False):
+ *   out[orow(r),:] = in[r,:] + alpha[0] * pe[pos(r), :], pos(r) = positions ? positions[r] : pos0 + r,
+ *   orow(r) = out_rows ? out_rows[r] : r   (pe = fp32 table built on the CPU,
+ *   embedding.py:75-91; product and sum rounded separately as the reference does). */
+int vb_add_pe(const float *in, int64_t in_row_stride, const float *pe, int64_t pos0,
+              const int32_t *positions, const float *alpha, int64_t n_rows, int d, float *out,
+              int64_t out_row_stride, const int32_t *out_rows, vb_stream_t stream);
+
+/* a8 / a9  LayerNorm.forward (transformer.py:57-74) and AdaptiveLayerNorm.forward
+ *   (transformer.py:93-108).  y = LN(x; gamma, beta, eps); if ada_wb != NULL:
+ *   y = ada_wb[0:d] * y + ada_wb[d:2d]  (weight | bias split order of transformer.py:96-101).
+ *   rows: optional gather list (device int32 [n_rows]) of source rows, NULL = identity.
+ *   out_dtype VB_F32 / VB_BF16. */
+int vb_layernorm(const float *x, int64_t x_row_stride, const int32_t *rows, int64_t n_rows, int d,
+                 const float *gamma, const float *beta, const float *ada_wb, float eps, void *out,
+                 int out_dtype, vb_stream_t stream);
+
+/* AdaptiveLayerNorm.project_layer for one stage embedding (transformer.py:96-100):
+ *   out[2d] = W[2d,d] * emb[d] + b[2d]   (fp32) */
+int vb_adaln_project(const float *W, const float *b, const float *emb, int d, float *out,
+                     vb_stream_t stream);
+
+/* a6/a7/a12  F.linear with fused epilogue (QKV in-proj, out-proj, FFN linear1/linear2,
+ *   predict layers; transformer.py:332-334, activation.py:408, valle.py:1039,1128):
+ *   C[M,N] = epi( A[M,K] * W[N,K]^T + bias[N] )
+ *   VB_EPI_NONE / VB_EPI_RELU: C has dtype c_dtype.  VB_EPI_RESIDUAL: C is fp32 and is
+ *   accumulated in place (C += ...), i.e. the residual add of transformer.py:297-302.
+ *   a_dtype must equal w_dtype.  bf16 operands use the tcgen05/TMEM kernel when M is large,
+ *   fp32 operands the exact-order SIMT kernel. */
+int vb_linear(const void *A, int a_dtype, int64_t lda, const void *W, int w_dtype, const float *bias,
+              void *C, int c_dtype, int64_t ldc, int64_t M, int N, int K, int epilogue,
+              void *workspace, size_t workspace_bytes, vb_stream_t stream);
+
+/* a7  scaled-dot-product attention of F.multi_head_attention_forward over packed, ragged
+ *   sequences.  qkv: [M, 3d] (Q|K|V column blocks, head h = columns [h*hd,(h+1)*hd) of each
+ *   block), cu_seqlens: device int32 [B+1] row offsets, text_lens: device int32 [B] (only for
+ *   VB_MASK_VALLE_AR).  out: [M, d].  If kcache != NULL the K and V rows are also written to
+ *   the caches ([B, H, cache_cap, hd], dtype = dtype) at their sequence position. */
+int vb_attention(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
+                 const int32_t *cu_seqlens, const int32_t *text_lens, int max_seqlen, int mask_mode,
+                 void *out, void *kcache, void *vcache, int64_t cache_seq_stride, int cache_cap,
+                 vb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Decoder stack handle (transformer.py:337-406 TransformerEncoder of pre-LN
+ * TransformerEncoderLayer, transformer.py:178-334).  Stores the caller's pointers only.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct vb_layer_params {
+  const void *in_proj_w;   /* [3d, d]  wdtype  self_attn.in_proj_weight */
+  const float *in_proj_b;  /* [3d]     f32 */
+  const void *out_proj_w;  /* [d, d] */
+  const float *out_proj_b; /* [d] */
+  const void *lin1_w;      /* [dff, d] */
+  const float *lin1_b;     /* [dff] */
+  const void *lin2_w;      /* [d, dff] */
+  const float *lin2_b;     /* [d] */
+  const float *norm1_w, *norm1_b; /* [d] LayerNorm affine (inner norm for AdaLN) */
+  const float *norm2_w, *norm2_b;
+} vb_layer_params;
+
+typedef struct vb_decoder_desc {
+  int32_t d_model, n_head, n_layer, d_ff;
+  int32_t wdtype;                /* vb_dtype of the matrices and of activations/KV cache */
+  const vb_layer_params *layers; /* host array [n_layer] */
+  const float *final_norm_w, *final_norm_b; /* [d] */
+} vb_decoder_desc;
+
+typedef struct vb_decoder *vb_decoder_t;
+
+int vb_decoder_create(const vb_decoder_desc *desc, vb_decoder_t *out);
+void vb_decoder_destroy(vb_decoder_t dec);
+
+/* bytes of scratch vb_decoder_forward needs for M rows */
+size_t vb_decoder_forward_workspace(const vb_decoder_desc *desc, int64_t M);
+
+/* a5/a6  TransformerEncoder.forward WITHOUT the final norm over packed ragged sequences
+ *   (prefill of the AR decoder, a NAR pass, the training forward).
+ *   x: fp32 [M, d] residual stream, updated in place.
+ *   ada_wb: NULL (LayerNorm) or fp32 [(2*n_layer+1), 2d] AdaLN (weight|bias) rows for the
+ *   current stage: row 2l = layer l norm1, 2l+1 = layer l norm2, last = final norm.
+ *   kcache/vcache: NULL or [n_layer, B, H, cache_cap, hd] caches filled for later decoding. */
+int vb_decoder_forward(vb_decoder_t dec, float *x, int64_t M, int B, const int32_t *cu_seqlens,
+                       const int32_t *text_lens, int max_seqlen, int mask_mode, const float *ada_wb,
+                       void *kcache, void *vcache, int64_t cache_layer_stride,
+                       int64_t cache_seq_stride, int cache_cap, void *workspace,
+                       size_t workspace_bytes, vb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a1  AR sampling loop of VALLE.inference (valle.py:1012-1057) with a growing KV cache,
+ *     batched over B independent utterances.  All loop state lives on the device.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct vb_ar_state {
+  int32_t B;
+  int32_t tok_stride;         /* row stride of `tokens` */
+  const int32_t *text_len;    /* [B] S_b */
+  const int32_t *prompt_len;  /* [B] Tp_b */
+  const int32_t *max_new;     /* [B] stop when n_gen > max_new (reference: 16*S_b, valle.py:1047) */
+  int32_t *n_gen;             /* [B] tokens generated so far */
+  int32_t *finished;          /* [B] 0 running, 1 stopped, 2 stopped at step 0 (valle.py:1049) */
+  int32_t *tokens;            /* [B, tok_stride] generated first-codebook ids */
+  float *x_cur;               /* [B, d] input row of the next decode step */
+  float *logits;              /* [B, n_vocab_pad] fp32 logits of the last step (for sampling) */
+  void *kcache, *vcache;      /* [n_layer, B, H, cache_cap, hd] */
+  int64_t cache_layer_stride, cache_seq_stride; /* in elements */
+  int32_t cache_cap;
+  int32_t n_active_out_unused;
+} vb_ar_state;
+
+typedef struct vb_ar_head {
+  const void *predict_w;      /* [n_vocab, d] ar_predict_layer.weight (wdtype), no bias */
+  int32_t n_vocab;            /* 1025 */
+  int32_t eos_id;             /* 1024 */
+  const float *audio_emb;     /* fp32 [n_vocab, d] ar_audio_embedding */
+  const float *alpha;         /* ar_audio_position.alpha (device scalar) */
+  const float *pe;            /* fp32 [pe_rows, d] sine table */
+  int32_t pe_rows;
+  int32_t greedy;             /* 1: argmax + stop rule + append on device; 0: logits only */
+} vb_ar_head;
+
+size_t vb_ar_step_workspace(const vb_decoder_desc *desc, int B, int cache_cap);
+
+/* final LayerNorm + ar_predict_layer on rows h[B,d] (valle.py:1039), then (greedy) the stop
+ * rule of valle.py:1044-1048 and the append of valle.py:1057 + next-row embedding
+ * (valle.py:1013-1015).  Used after prefill and at the end of every decode step. */
+int vb_ar_head_step(vb_decoder_t dec, const vb_ar_head *head, const float *h, vb_ar_state *st,
+                    void *workspace, size_t workspace_bytes, vb_stream_t stream);
+
+/* one decode step for all B rows: 12 x (LN -> QKV -> KV append -> single-query attention over
+ * the cache -> out-proj -> LN -> FFN), then vb_ar_head_step.  Safe to capture in a CUDA graph
+ * (no host reads; launch geometry depends only on B and cache_cap). */
+int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_state *st, void *workspace,
+                      size_t workspace_bytes, vb_stream_t stream);
+
+/* after sampling on the host side (top_k != 1): push tokens[B] chosen by the caller
+ * (valle.py:1040-1057 with torch's own RNG), applying the same stop rule. */
+int vb_ar_push_tokens(const vb_ar_head *head, vb_ar_state *st, const int64_t *sampled, int d,
+                      vb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a1  NAR stage tail (valle.py:1128-1134): samples = argmax(logits) over rows, written to
+ *     codes[r*code_row_stride] (int64), and (if next_emb != NULL) y_emb[yrow(r),:] += next_emb[sample],
+ *     yrow(r) = y_rows ? y_rows[r] : r.
+ * ---------------------------------------------------------------------------------------- */
+int vb_nar_argmax_accumulate(const float *logits, int64_t n_rows, int n_vocab, int64_t ld_logits,
+                             int64_t *codes, int64_t code_row_stride, const float *next_emb,
+                             float *y_emb, int64_t y_row_stride, const int32_t *y_rows, int d,
+                             vb_stream_t stream);
+
+/* gather rows: dst[r,:] = src[rows[r],:]  (fp32), used for "last position" / target slices */
+int vb_gather_rows(const float *src, int64_t src_row_stride, const int32_t *rows, int64_t n_rows,
+                   int d, float *dst, int64_t dst_row_stride, vb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VALLE_B200_H_ */

@@ -1,0 +1,45 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+def load_golden(name):
+    import torch
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def build_model(cfg, seed, device="cpu"):
+    """valle_b200 VALLE with the reference's default init under torch.manual_seed(seed)."""
+    import torch
+    from valle_b200.models import VALLE
+    torch.manual_seed(seed)
+    m = VALLE(cfg["d_model"], cfg["nhead"], cfg["num_layers"], norm_first=True, add_prenet=False,
+              prefix_mode=cfg["prefix_mode"], share_embedding=True, nar_scale_factor=1.0,
+              prepend_bos=False, num_quantizers=cfg["num_quantizers"]).eval()
+    return m.to(device)
+
+
+def assert_checksums(model, ck):
+    import torch
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(ck.keys())
+    for k, v in sd.items():
+        got = torch.stack([v.double().sum(), v.double().abs().sum()]).cpu()
+        assert torch.equal(got, ck[k]), f"weights differ from the reference init at {k}"
+
+
+@pytest.fixture(scope="session")
+def lib():
+    from valle_b200 import _lib
+    return _lib.load()

@@ -1,0 +1,197 @@
+// C-ABI entry points and host-side orchestration (layer loops) of libvalle_b200.so.
+// See include/valle_b200.h for the contract of every function.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vb {
+
+static thread_local char g_err[1024] = "";
+static int64_t g_launches = 0;  // process-wide counter (relaxed; bench reads it when idle)
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED); }
+
+}  // namespace vb
+
+using namespace vb;
+
+struct vb_decoder {
+  vb_decoder_desc desc;
+  vb_layer_params *layers;  // owned host copy
+};
+
+VB_API int vb_abi_version(void) { return VB_ABI_VERSION; }
+VB_API const char *vb_last_error(void) { return g_err; }
+VB_API int64_t vb_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+VB_API int vb_linear(const void *A, int a_dtype, int64_t lda, const void *W, int w_dtype,
+                         const float *bias, void *C, int c_dtype, int64_t ldc, int64_t M, int N, int K,
+                         int epilogue, void *workspace, size_t workspace_bytes, vb_stream_t stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  VB_CHECK_ARG(a_dtype == w_dtype, "vb_linear: a_dtype (%d) must equal w_dtype (%d)", a_dtype, w_dtype);
+  VB_CHECK_ARG(epilogue >= VB_EPI_NONE && epilogue <= VB_EPI_RESIDUAL, "vb_linear: bad epilogue %d", epilogue);
+  VB_CHECK_ARG(M >= 0 && N > 0 && K > 0, "vb_linear: bad shape M=%lld N=%d K=%d", (long long)M, N, K);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a_dtype == VB_BF16 && tcgen05_gemm_supported(M, N, K, lda, ldc))
+    return launch_gemm_tcgen05((const bf16 *)A, lda, (const bf16 *)W, bias, C, c_dtype, ldc, M, N, K,
+                               epilogue, s);
+  return launch_gemm_simt(A, a_dtype, lda, W, bias, C, c_dtype, ldc, M, N, K, epilogue, s);
+}
+
+VB_API int vb_decoder_create(const vb_decoder_desc *desc, vb_decoder_t *out) {
+  VB_CHECK_ARG(desc && out, "vb_decoder_create: null argument");
+  VB_CHECK_ARG(desc->n_layer > 0 && desc->n_head > 0 && desc->d_model % desc->n_head == 0,
+               "vb_decoder_create: bad geometry d=%d H=%d L=%d", desc->d_model, desc->n_head, desc->n_layer);
+  VB_CHECK_ARG(desc->d_model / desc->n_head == 64, "vb_decoder_create: head_dim must be 64 (got %d)",
+               desc->d_model / desc->n_head);
+  VB_CHECK_ARG(desc->d_model % 256 == 0 && desc->d_ff % 256 == 0, "vb_decoder_create: d_model and d_ff must be multiples of 256");
+  VB_CHECK_ARG(desc->wdtype == VB_F32 || desc->wdtype == VB_BF16, "vb_decoder_create: bad wdtype");
+  vb_decoder *d = new (std::nothrow) vb_decoder;
+  if (!d) {
+    set_error("vb_decoder_create: out of host memory");
+    return VB_ERR_ARG;
+  }
+  d->desc = *desc;
+  d->layers = new (std::nothrow) vb_layer_params[desc->n_layer];
+  memcpy(d->layers, desc->layers, sizeof(vb_layer_params) * desc->n_layer);
+  d->desc.layers = d->layers;
+  *out = d;
+  return VB_OK;
+}
+
+VB_API void vb_decoder_destroy(vb_decoder_t dec) {
+  if (!dec) return;
+  delete[] dec->layers;
+  delete dec;
+}
+
+static size_t elem_size(int dtype) { return dtype == VB_BF16 ? 2 : 4; }
+
+VB_API size_t vb_decoder_forward_workspace(const vb_decoder_desc *desc, int64_t M) {
+  const size_t ts = elem_size(desc->wdtype);
+  const size_t d = desc->d_model, dff = desc->d_ff;
+  const size_t Mp = align_up((size_t)M, 128);
+  return Mp * (d + 3 * d + d + dff) * ts + 4 * 256;
+}
+
+VB_API int vb_decoder_forward(vb_decoder_t dec, float *x, int64_t M, int B, const int32_t *cu_seqlens,
+                                  const int32_t *text_lens, int max_seqlen, int mask_mode,
+                                  const float *ada_wb, void *kcache, void *vcache,
+                                  int64_t cache_layer_stride, int64_t cache_seq_stride, int cache_cap,
+                                  void *workspace, size_t workspace_bytes, vb_stream_t stream) {
+  VB_CHECK_ARG(dec && x && cu_seqlens, "vb_decoder_forward: null argument");
+  const vb_decoder_desc &D = dec->desc;
+  VB_CHECK_ARG(workspace_bytes >= vb_decoder_forward_workspace(&D, M),
+               "vb_decoder_forward: workspace too small (%zu < %zu)", workspace_bytes,
+               vb_decoder_forward_workspace(&D, M));
+  if (M == 0) return VB_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int d = D.d_model, dff = D.d_ff, dt = D.wdtype;
+  const size_t ts = elem_size(dt);
+  const size_t Mp = align_up((size_t)M, 128);
+  char *ws = (char *)workspace;
+  void *xn = ws;   ws += align_up(Mp * d * ts, 256);
+  void *qkv = ws;  ws += align_up(Mp * 3 * d * ts, 256);
+  void *att = ws;  ws += align_up(Mp * d * ts, 256);
+  void *hb = ws;
+  for (int l = 0; l < D.n_layer; ++l) {
+    const vb_layer_params &P = dec->layers[l];
+    const float *ada1 = ada_wb ? ada_wb + (size_t)(2 * l) * 2 * d : nullptr;
+    const float *ada2 = ada_wb ? ada_wb + (size_t)(2 * l + 1) * 2 * d : nullptr;
+    VB_TRY(vb_layernorm(x, d, nullptr, M, d, P.norm1_w, P.norm1_b, ada1, 1e-5f, xn, dt, stream));
+    VB_TRY(vb_linear(xn, dt, d, P.in_proj_w, dt, P.in_proj_b, qkv, dt, 3 * d, M, 3 * d, d, VB_EPI_NONE,
+                     nullptr, 0, stream));
+    void *kc = kcache ? (char *)kcache + (size_t)l * cache_layer_stride * ts : nullptr;
+    void *vc = vcache ? (char *)vcache + (size_t)l * cache_layer_stride * ts : nullptr;
+    VB_TRY(launch_attention_varlen(qkv, dt, M, B, D.n_head, d / D.n_head, cu_seqlens, text_lens, max_seqlen,
+                                   mask_mode, att, kc, vc, cache_seq_stride, cache_cap, s));
+    VB_TRY(vb_linear(att, dt, d, P.out_proj_w, dt, P.out_proj_b, x, VB_F32, d, M, d, d, VB_EPI_RESIDUAL,
+                     nullptr, 0, stream));
+    VB_TRY(vb_layernorm(x, d, nullptr, M, d, P.norm2_w, P.norm2_b, ada2, 1e-5f, xn, dt, stream));
+    VB_TRY(vb_linear(xn, dt, d, P.lin1_w, dt, P.lin1_b, hb, dt, dff, M, dff, d, VB_EPI_RELU, nullptr, 0,
+                     stream));
+    VB_TRY(vb_linear(hb, dt, dff, P.lin2_w, dt, P.lin2_b, x, VB_F32, d, M, d, dff, VB_EPI_RESIDUAL, nullptr,
+                     0, stream));
+  }
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// AR decode
+// ------------------------------------------------------------------------------------------
+VB_API size_t vb_ar_step_workspace(const vb_decoder_desc *desc, int B, int cache_cap) {
+  const size_t d = desc->d_model, dff = desc->d_ff;
+  size_t n = 0;
+  n += align_up((size_t)B * d * 4, 256);    // q
+  n += align_up((size_t)B * d * 4, 256);    // att
+  n += align_up((size_t)B * dff * 4, 256);  // ffn hidden
+  n += align_up(attn_decode_workspace(B, desc->n_head, (int)(d / desc->n_head), cache_cap), 256);
+  return n + 256;
+}
+
+VB_API int vb_ar_head_step(vb_decoder_t dec, const vb_ar_head *head, const float *h, vb_ar_state *st,
+                               void *workspace, size_t workspace_bytes, vb_stream_t stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  VB_CHECK_ARG(dec && head && h && st, "vb_ar_head_step: null argument");
+  const vb_decoder_desc &D = dec->desc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int d = D.d_model;
+  const int ldl = (head->n_vocab + 3) & ~3;
+  LnParams ln{D.final_norm_w, D.final_norm_b, nullptr, 1e-5f};
+  VB_TRY(launch_gemv(h, d, st->B, head->predict_w, D.wdtype, nullptr, head->n_vocab, d, st->logits, ldl,
+                     &ln, 0, nullptr, s));
+  if (head->greedy) VB_TRY(launch_ar_sample(st->logits, ldl, head, st, d, nullptr, s));
+  return VB_OK;
+}
+
+VB_API int vb_ar_push_tokens(const vb_ar_head *head, vb_ar_state *st, const int64_t *sampled, int d,
+                                 vb_stream_t stream) {
+  VB_CHECK_ARG(head && st && sampled, "vb_ar_push_tokens: null argument");
+  const int ldl = (head->n_vocab + 3) & ~3;
+  return launch_ar_sample(st->logits, ldl, head, st, d, sampled, (cudaStream_t)stream);
+}
+
+VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_state *st, void *workspace,
+                                 size_t workspace_bytes, vb_stream_t stream) {
+  VB_CHECK_ARG(dec && head && st, "vb_ar_decode_step: null argument");
+  const vb_decoder_desc &D = dec->desc;
+  VB_CHECK_ARG(workspace_bytes >= vb_ar_step_workspace(&D, st->B, st->cache_cap),
+               "vb_ar_decode_step: workspace too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int d = D.d_model, dff = D.d_ff, B = st->B, dt = D.wdtype;
+  const size_t ts = elem_size(dt);
+  char *ws = (char *)workspace;
+  float *q = (float *)ws;    ws += align_up((size_t)B * d * 4, 256);
+  float *att = (float *)ws;  ws += align_up((size_t)B * d * 4, 256);
+  float *hb = (float *)ws;   ws += align_up((size_t)B * dff * 4, 256);
+  void *aws = ws;
+  float *x = st->x_cur;
+  for (int l = 0; l < D.n_layer; ++l) {
+    const vb_layer_params &P = dec->layers[l];
+    void *kc = (char *)st->kcache + (size_t)l * st->cache_layer_stride * ts;
+    void *vc = (char *)st->vcache + (size_t)l * st->cache_layer_stride * ts;
+    LnParams ln1{P.norm1_w, P.norm1_b, nullptr, 1e-5f};
+    QkvScatter sc{d, d / D.n_head, q, kc, vc, st->cache_seq_stride, st->cache_cap,
+                  st->text_len, st->prompt_len, st->n_gen};
+    VB_TRY(launch_gemv(x, d, B, P.in_proj_w, dt, P.in_proj_b, 3 * d, d, nullptr, 0, &ln1, 3, &sc, s));
+    VB_TRY(launch_attn_decode(q, B, D.n_head, d / D.n_head, kc, vc, dt, st->cache_seq_stride, st->cache_cap,
+                              st->text_len, st->prompt_len, st->n_gen, att, aws, s));
+    VB_TRY(launch_gemv(att, d, B, P.out_proj_w, dt, P.out_proj_b, d, d, x, d, nullptr, 2, nullptr, s));
+    LnParams ln2{P.norm2_w, P.norm2_b, nullptr, 1e-5f};
+    VB_TRY(launch_gemv(x, d, B, P.lin1_w, dt, P.lin1_b, dff, d, hb, dff, &ln2, 1, nullptr, s));
+    VB_TRY(launch_gemv(hb, dff, B, P.lin2_w, dt, P.lin2_b, d, dff, x, d, nullptr, 2, nullptr, s));
+  }
+  return vb_ar_head_step(dec, head, x, st, nullptr, 0, stream);
+}

@@ -1,0 +1,395 @@
+// Attention kernels (head_dim = 64).
+//   * attn_varlen_simt : softmax(q k^T / 8 + mask) v over packed ragged sequences, fp32 math in a
+//     fixed order -- prefill of the AR decoder, NAR passes and the training forward in fp32
+//     parity mode.  Also fills the KV cache.
+//   * attn_decode      : one query row per (utterance, head) against the growing KV cache.
+//     HBM-bound: 16-byte coalesced K/V reads, warp-shuffle dot products and softmax
+//     reductions, split-KV across CTAs when B*H is too small to fill 148 SMs.
+//
+// Reference arithmetic: F.multi_head_attention_forward as called from
+// valle/modules/activation.py:408-427; masks valle/models/valle.py:1010-1033 (AR) / none (NAR).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vb {
+
+static constexpr int HD = 64;
+
+// ------------------------------------------------------------------------------------------
+// Ragged multi-query attention, 64x64 tiles, 256 threads, 4x4 micro-tiles.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__restrict__ cu_seqlens,
+                        const int32_t *__restrict__ text_lens, int mask_mode, T *__restrict__ out,
+                        T *__restrict__ kcache, T *__restrict__ vcache, int64_t cache_seq_stride,
+                        int cache_cap) {
+  constexpr int LDT = 68;  // padded leading dim (floats), keeps float4 alignment
+  extern __shared__ __align__(16) float smem[];
+  float *Qt = smem;             // [64 e][LDT rows]
+  float *Kt = Qt + 64 * LDT;    // [64 e][LDT keys]
+  float *Vs = Kt + 64 * LDT;    // [64 keys][LDT e]
+  float *Pt = Vs + 64 * LDT;    // [64 keys][LDT rows]
+
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int r0 = cu_seqlens[b], L = cu_seqlens[b + 1] - r0;
+  const int q0 = blockIdx.x * 64;
+  if (q0 >= L) return;
+  const int S = (mask_mode == VB_MASK_VALLE_AR) ? text_lens[b] : 0;
+  const int d = n_head * HD;
+  const int64_t ld = 3 * (int64_t)d;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lrow = tid >> 2, le0 = (tid & 3) * 16;
+
+  // load Q tile (transposed)
+  {
+    const int qr = q0 + lrow;
+    const T *src = qkv + (int64_t)(r0 + min(qr, L - 1)) * ld + h * HD + le0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) Qt[(le0 + i) * LDT + lrow] = (qr < L) ? to_f32(src[i]) : 0.f;
+  }
+  int lim[4];  // kv_len per owned row
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qr = q0 + ty * 4 + i;
+    lim[i] = qr >= L ? 0 : (mask_mode == VB_MASK_VALLE_AR ? max(S, qr + 1) : L);
+  }
+  const int q_hi = min(q0 + 64, L);
+  const int kv_max = (mask_mode == VB_MASK_VALLE_AR) ? max(S, q_hi) : L;
+
+  float m_run[4], l_run[4], o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -CUDART_INF_F;
+    l_run[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  }
+
+  for (int j0 = 0; j0 < kv_max; j0 += 64) {
+    __syncthreads();  // previous tile fully consumed (also covers the Q store above)
+    {
+      const int kr = j0 + lrow;
+      const bool ok = kr < L;
+      const T *ksrc = qkv + (int64_t)(r0 + min(kr, L - 1)) * ld + d + h * HD + le0;
+      const T *vsrc = ksrc + d;
+      T kraw[16], vraw[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        kraw[i] = ksrc[i];
+        vraw[i] = vsrc[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        Kt[(le0 + i) * LDT + lrow] = ok ? to_f32(kraw[i]) : 0.f;
+        Vs[lrow * LDT + le0 + i] = ok ? to_f32(vraw[i]) : 0.f;
+      }
+      if (kcache != nullptr && j0 == q0 && ok) {  // this CTA owns rows [q0, q0+64) of the cache
+        const int64_t off = (int64_t)b * cache_seq_stride + ((int64_t)h * cache_cap + kr) * HD + le0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          kcache[off + i] = kraw[i];
+          vcache[off + i] = vraw[i];
+        }
+      }
+    }
+    __syncthreads();
+    // S = Q K^T
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+    for (int e = 0; e < HD; ++e) {
+      const float4 qa = *reinterpret_cast<const float4 *>(&Qt[e * LDT + ty * 4]);
+      const float4 kb = *reinterpret_cast<const float4 *>(&Kt[e * LDT + tx * 4]);
+      const float qv[4] = {qa.x, qa.y, qa.z, qa.w};
+      const float kv[4] = {kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qv[i], kv[j], s[i][j]);
+    }
+    // online softmax per row (16 lanes share a row)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = j0 + tx * 4 + j;
+        s[i][j] = (c < lim[i]) ? s[i][j] * 0.125f : -CUDART_INF_F;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float m_new = fmaxf(m_run[i], mx);
+      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
+      const float corr = expf(m_run[i] - m_use);  // exp(-inf) = 0 on the first tile
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = expf(s[i][j] - m_use);
+        rs += s[i][j];
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+      l_run[i] = l_run[i] * corr + rs;
+      m_run[i] = m_new;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] *= corr;
+    }
+    // P^T to shared: Pt[key][row]
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4 *>(&Pt[(tx * 4 + j) * LDT + ty * 4]) =
+          make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
+    __syncthreads();
+    // O += P V
+#pragma unroll 8
+    for (int c = 0; c < 64; ++c) {
+      const float4 pa = *reinterpret_cast<const float4 *>(&Pt[c * LDT + ty * 4]);
+      const float4 vb4 = *reinterpret_cast<const float4 *>(&Vs[c * LDT + tx * 4]);
+      const float pv[4] = {pa.x, pa.y, pa.z, pa.w};
+      const float vv[4] = {vb4.x, vb4.y, vb4.z, vb4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = fmaf(pv[i], vv[j], o[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qr = q0 + ty * 4 + i;
+    if (qr >= L) continue;
+    const float inv = 1.f / l_run[i];
+    T *dst = out + (int64_t)(r0 + qr) * d + h * HD + tx * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dst[j] = from_f32<T>(o[i][j] * inv);
+  }
+}
+
+int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
+                            const int32_t *cu_seqlens, const int32_t *text_lens, int max_seqlen,
+                            int mask_mode, void *out, void *kcache, void *vcache,
+                            int64_t cache_seq_stride, int cache_cap, cudaStream_t s) {
+  VB_CHECK_ARG(head_dim == HD, "attention: head_dim=%d, only 64 is built", head_dim);
+  VB_CHECK_ARG(mask_mode == VB_MASK_FULL || text_lens != nullptr, "attention: AR mask needs text_lens");
+  if (M == 0 || B == 0) return VB_OK;
+  const size_t smem = 4 * 64 * 68 * sizeof(float);
+  dim3 grid((max_seqlen + 63) / 64, n_head, B);
+  if (dtype == VB_F32) {
+    auto k = attn_varlen_simt_kernel<float>;
+    VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, s>>>((const float *)qkv, n_head, cu_seqlens, text_lens, mask_mode, (float *)out,
+                              (float *)kcache, (float *)vcache, cache_seq_stride, cache_cap);
+  } else if (dtype == VB_BF16) {
+    auto k = attn_varlen_simt_kernel<bf16>;
+    VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, 256, smem, s>>>((const bf16 *)qkv, n_head, cu_seqlens, text_lens, mask_mode, (bf16 *)out,
+                              (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap);
+  } else {
+    set_error("attention: bad dtype %d", dtype);
+    return VB_ERR_ARG;
+  }
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Single-query decode attention over the KV cache.
+//   grid (H, B, nsplit), 128 threads.  kv_len[b] = S_b + Tp_b + n_gen[b].
+// ------------------------------------------------------------------------------------------
+static constexpr int kDecMaxChunk = 4096;
+
+template <typename T> struct KvRow8 {  // 8 consecutive elements of a cache row as floats
+  static __device__ __forceinline__ void load(const T *p, float (&f)[8]);
+};
+template <> __device__ __forceinline__ void KvRow8<float>::load(const float *p, float (&f)[8]) {
+  const uint4 a = ldg_stream16(p), b = ldg_stream16(p + 4);
+  f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+  f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+}
+template <> __device__ __forceinline__ void KvRow8<bf16>::load(const bf16 *p, float (&f)[8]) {
+  Vec16<bf16> v;
+  v.raw = ldg_stream16(p);
+  v.unpack(f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+attn_decode_kernel(const float *__restrict__ q, int n_head, const T *__restrict__ kcache,
+                   const T *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
+                   const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
+                   const int32_t *__restrict__ n_gen, float *__restrict__ out, float *__restrict__ part_o,
+                   float *__restrict__ part_ml, int nsplit) {
+  __shared__ float sc[kDecMaxChunk];
+  __shared__ __align__(16) float qs[HD];
+  __shared__ float red[16][HD + 1];
+  __shared__ float wred[8];
+  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = n_head * HD;
+  int kv_len = text_len[b] + prompt_len[b] + n_gen[b];
+  kv_len = max(1, min(kv_len, cache_cap));
+  const int chunk = ((kv_len + nsplit - 1) / nsplit + 15) & ~15;
+  const int c0 = sp * chunk, c1 = min(kv_len, c0 + chunk);
+  const int n = max(0, c1 - c0);
+  const T *kb = kcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
+  const T *vb_ = vcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
+  if (tid < HD) qs[tid] = q[(int64_t)b * d + h * HD + tid] * 0.125f;
+  __syncthreads();
+
+  // ---- scores: 8 lanes per key, 4 keys per warp-iteration, 16 keys per CTA-iteration ----
+  const int g = lane >> 3, j8 = (lane & 7) * 8;
+  float qf[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qf[i] = qs[j8 + i];
+  float lmax = -CUDART_INF_F;
+  for (int base = 0; base < n; base += 64) {
+    float kf[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = base + u * 16 + warp * 4 + g;
+      const int kk = min(key, n - 1);
+      KvRow8<T>::load(kb + (int64_t)(c0 + kk) * HD + j8, kf[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = base + u * 16 + warp * 4 + g;
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], kf[u][i], dot);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      if ((lane & 7) == 0 && key < n) {
+        sc[key] = dot;
+        lmax = fmaxf(lmax, dot);
+      }
+    }
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) wred[warp] = lmax;
+  __syncthreads();
+  const float m = fmaxf(fmaxf(wred[0], wred[1]), fmaxf(wred[2], wred[3]));
+  float lsum = 0.f;
+  for (int i = tid; i < n; i += 128) {
+    const float p = expf(sc[i] - m);
+    sc[i] = p;
+    lsum += p;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) wred[4 + warp] = lsum;
+  __syncthreads();
+  const float l = (wred[4] + wred[5]) + (wred[6] + wred[7]);
+
+  // ---- O = P V : thread = (element group eg, key lane jl) --------------------------------
+  const int eg = (tid & 7) * 8, jl = tid >> 3;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int base = 0; base < n; base += 64) {
+    float vf[4][8];
+    float pv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = base + u * 16 + jl;
+      const int kk = min(key, n - 1);
+      pv[u] = key < n ? sc[kk] : 0.f;
+      KvRow8<T>::load(vb_ + (int64_t)(c0 + kk) * HD + eg, vf[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(pv[u], vf[u][i], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[jl][eg + i] = acc[i];
+  __syncthreads();
+  if (tid < HD) {
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) s += red[r][tid];
+    if (nsplit == 1) {
+      out[(int64_t)b * d + h * HD + tid] = s / l;
+    } else {
+      const int64_t pi = ((int64_t)b * n_head + h) * nsplit + sp;
+      part_o[pi * HD + tid] = s;
+      if (tid == 0) {
+        part_ml[pi * 2] = n > 0 ? m : -CUDART_INF_F;
+        part_ml[pi * 2 + 1] = n > 0 ? l : 0.f;
+      }
+    }
+  }
+}
+
+__global__ void attn_decode_combine_kernel(const float *__restrict__ part_o,
+                                           const float *__restrict__ part_ml, int n_head, int nsplit,
+                                           float *__restrict__ out) {
+  const int h = blockIdx.x, b = blockIdx.y, e = threadIdx.x;
+  const int64_t p0 = ((int64_t)b * n_head + h) * nsplit;
+  float m = -CUDART_INF_F;
+  for (int s = 0; s < nsplit; ++s) m = fmaxf(m, part_ml[(p0 + s) * 2]);
+  float l = 0.f, o = 0.f;
+  for (int s = 0; s < nsplit; ++s) {
+    const float ms = part_ml[(p0 + s) * 2];
+    if (ms == -CUDART_INF_F) continue;
+    const float w = expf(ms - m);
+    l += part_ml[(p0 + s) * 2 + 1] * w;
+    o += part_o[(p0 + s) * HD + e] * w;
+  }
+  out[(int64_t)b * n_head * HD + h * HD + e] = o / l;
+}
+
+static int decode_nsplit(int B, int n_head, int cache_cap) {
+  int ns = (2 * sm_count() + B * n_head - 1) / (B * n_head);
+  ns = max(1, min(ns, 32));
+  ns = min(ns, max(1, cache_cap / 64));              // keep chunks >= 64 keys
+  ns = max(ns, (cache_cap + kDecMaxChunk - 1) / kDecMaxChunk);  // chunk must fit the score buffer
+  return ns;
+}
+
+size_t attn_decode_workspace(int B, int n_head, int head_dim, int cache_cap) {
+  const int ns = decode_nsplit(B, n_head, cache_cap);
+  return (size_t)B * n_head * ns * (head_dim + 2) * sizeof(float) + 256;
+}
+
+int launch_attn_decode(const float *q, int B, int n_head, int head_dim, const void *kcache,
+                       const void *vcache, int dtype, int64_t cache_seq_stride, int cache_cap,
+                       const int32_t *text_len, const int32_t *prompt_len, const int32_t *n_gen,
+                       float *out, void *workspace, cudaStream_t s) {
+  VB_CHECK_ARG(head_dim == HD, "attn_decode: head_dim=%d, only 64 is built", head_dim);
+  const int ns = decode_nsplit(B, n_head, cache_cap);
+  VB_CHECK_ARG((cache_cap + ns - 1) / ns + 16 <= kDecMaxChunk, "attn_decode: cache_cap %d too large", cache_cap);
+  float *part_o = (float *)workspace;
+  float *part_ml = part_o + (size_t)B * n_head * ns * HD;
+  dim3 grid(n_head, B, ns);
+  if (dtype == VB_F32)
+    attn_decode_kernel<float><<<grid, 128, 0, s>>>(q, n_head, (const float *)kcache, (const float *)vcache,
+                                                   cache_seq_stride, cache_cap, text_len, prompt_len, n_gen,
+                                                   out, part_o, part_ml, ns);
+  else
+    attn_decode_kernel<bf16><<<grid, 128, 0, s>>>(q, n_head, (const bf16 *)kcache, (const bf16 *)vcache,
+                                                  cache_seq_stride, cache_cap, text_len, prompt_len, n_gen,
+                                                  out, part_o, part_ml, ns);
+  VB_LAUNCH_CHECK();
+  if (ns > 1) {
+    attn_decode_combine_kernel<<<dim3(n_head, B), HD, 0, s>>>(part_o, part_ml, n_head, ns, out);
+    VB_LAUNCH_CHECK();
+  }
+  return VB_OK;
+}
+
+}  // namespace vb
+
+VB_API int vb_attention(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
+                            const int32_t *cu_seqlens, const int32_t *text_lens, int max_seqlen,
+                            int mask_mode, void *out, void *kcache, void *vcache,
+                            int64_t cache_seq_stride, int cache_cap, vb_stream_t stream) {
+  return vb::launch_attention_varlen(qkv, dtype, M, B, n_head, head_dim, cu_seqlens, text_lens, max_seqlen,
+                                     mask_mode, out, kcache, vcache, cache_seq_stride, cache_cap,
+                                     (cudaStream_t)stream);
+}

@@ -1,0 +1,141 @@
+// Device-side tails of the AR loop and of a NAR stage.
+//   * ar_sample_kernel: argmax over the 1025 logits, the stop rule of valle/models/valle.py:1044-1048
+//     (argmax==EOS or sample==EOS or n_new > 16*S), the append of :1057 and the embedding + sine PE
+//     of the appended token (:1013-1015) so the next decode step needs no host round trip
+//     (the reference syncs to the host once per token).
+//   * nar_argmax_accumulate_kernel: samples = argmax(logits) (:1130) and
+//     y_emb[:, Tp:] += nar_audio_embeddings[i+1](samples) (:1133-1134).
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace vb {
+
+struct ArgMax {
+  float v;
+  int i;
+};
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {
+  // larger value wins; on ties the smaller index (torch.argmax returns the first maximum)
+  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax b;
+    b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = better(a, b);
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(256)
+ar_sample_kernel(const float *__restrict__ logits, int64_t ld_logits, int n_vocab, int eos_id,
+                 const float *__restrict__ audio_emb, const float *__restrict__ alpha,
+                 const float *__restrict__ pe, int pe_rows, const int32_t *__restrict__ text_len,
+                 const int32_t *__restrict__ prompt_len, const int32_t *__restrict__ max_new,
+                 int32_t *__restrict__ n_gen, int32_t *__restrict__ finished,
+                 int32_t *__restrict__ tokens, int tok_stride, float *__restrict__ x_cur, int d,
+                 const int64_t *__restrict__ forced) {
+  __shared__ ArgMax wbest[8];
+  __shared__ int s_tok, s_pos;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (finished[b] != 0) return;  // uniform per CTA
+  const float *row = logits + (int64_t)b * ld_logits;
+  ArgMax best{-CUDART_INF_F, 0x7fffffff};
+  for (int i = tid; i < n_vocab; i += 256) best = better(best, ArgMax{row[i], i});
+  best = warp_argmax(best);
+  if (lane == 0) wbest[warp] = best;
+  __syncthreads();
+  if (tid == 0) {
+    ArgMax a = wbest[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) a = better(a, wbest[w]);
+    const int n_new = n_gen[b];
+    const int samp = forced ? (int)forced[b] : a.i;
+    const bool stop = (a.i == eos_id) || (samp == eos_id) || (n_new > max_new[b]) || (n_new >= tok_stride);
+    if (stop) {
+      finished[b] = (n_new == 0) ? 2 : 1;
+      s_tok = -1;
+    } else {
+      tokens[(int64_t)b * tok_stride + n_new] = samp;
+      n_gen[b] = n_new + 1;
+      s_tok = samp;
+      s_pos = min(prompt_len[b] + n_new, pe_rows - 1);
+    }
+  }
+  __syncthreads();
+  const int tok = s_tok;
+  if (tok < 0) return;
+  const float a = alpha[0];
+  const float *e = audio_emb + (int64_t)tok * d;
+  const float *p = pe + (int64_t)s_pos * d;
+  float *xo = x_cur + (int64_t)b * d;
+  for (int c = tid * 4; c < d; c += 1024) {
+    const float4 ev = *reinterpret_cast<const float4 *>(e + c);
+    const float4 pv = *reinterpret_cast<const float4 *>(p + c);
+    float4 o;
+    o.x = __fadd_rn(ev.x, __fmul_rn(a, pv.x));
+    o.y = __fadd_rn(ev.y, __fmul_rn(a, pv.y));
+    o.z = __fadd_rn(ev.z, __fmul_rn(a, pv.z));
+    o.w = __fadd_rn(ev.w, __fmul_rn(a, pv.w));
+    *reinterpret_cast<float4 *>(xo + c) = o;
+  }
+}
+
+int launch_ar_sample(const float *logits, int64_t ld_logits, const vb_ar_head *head, vb_ar_state *st,
+                     int d, const int64_t *forced, cudaStream_t s) {
+  ar_sample_kernel<<<st->B, 256, 0, s>>>(logits, ld_logits, head->n_vocab, head->eos_id, head->audio_emb,
+                                         head->alpha, head->pe, head->pe_rows, st->text_len,
+                                         st->prompt_len, st->max_new, st->n_gen, st->finished, st->tokens,
+                                         st->tok_stride, st->x_cur, d, forced);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+__global__ void nar_argmax_accumulate_kernel(const float *__restrict__ logits, int64_t n_rows, int n_vocab,
+                                             int64_t ld_logits, int64_t *__restrict__ codes,
+                                             int64_t code_row_stride, const float *__restrict__ next_emb,
+                                             float *__restrict__ y_emb, int64_t y_row_stride,
+                                             const int32_t *__restrict__ y_rows, int d) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const float *row = logits + r * ld_logits;
+  ArgMax best{-CUDART_INF_F, 0x7fffffff};
+  for (int i = lane; i < n_vocab; i += 32) best = better(best, ArgMax{row[i], i});
+  best = warp_argmax(best);
+  if (lane == 0) codes[r * code_row_stride] = best.i;
+  if (next_emb != nullptr) {
+    const float *e = next_emb + (int64_t)best.i * d;
+    float *y = y_emb + (y_rows ? (int64_t)y_rows[r] : r) * y_row_stride;
+    for (int c = lane * 4; c < d; c += 128) {
+      float4 yv = *reinterpret_cast<float4 *>(y + c);
+      const float4 ev = *reinterpret_cast<const float4 *>(e + c);
+      yv.x = __fadd_rn(yv.x, ev.x);
+      yv.y = __fadd_rn(yv.y, ev.y);
+      yv.z = __fadd_rn(yv.z, ev.z);
+      yv.w = __fadd_rn(yv.w, ev.w);
+      *reinterpret_cast<float4 *>(y + c) = yv;
+    }
+  }
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+VB_API int vb_nar_argmax_accumulate(const float *logits, int64_t n_rows, int n_vocab, int64_t ld_logits,
+                                        int64_t *codes, int64_t code_row_stride, const float *next_emb,
+                                        float *y_emb, int64_t y_row_stride, const int32_t *y_rows, int d,
+                                        vb_stream_t stream) {
+  VB_CHECK_ARG(d % 4 == 0, "vb_nar_argmax_accumulate: d %% 4 != 0");
+  if (n_rows == 0) return VB_OK;
+  const int wpb = 4;
+  nar_argmax_accumulate_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      logits, n_rows, n_vocab, ld_logits, codes, code_row_stride, next_emb, y_emb, y_row_stride, y_rows, d);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}

@@ -1,0 +1,403 @@
+"""Batched VALL-E decoding engine: the host side of the hot path.
+
+Implements the loops of `VALLE.inference` (valle/models/valle.py:961-1137) for B independent
+utterances at once on one GPU:
+
+  * AR: ragged prefill of text + acoustic prompt (fills the KV cache), then single-row decode
+    steps against the growing KV cache (the reference recomputes the whole sequence per token,
+    valle.py:1004 TODO).  The KV cache is exact under the reference's mask: text rows attend to
+    text only, audio rows to text + causal audio (valle.py:1019-1030), so cached K/V never change.
+    All loop state (lengths, tokens, stop flags) lives on the device; a decode step is one CUDA
+    graph replay; the host only polls the stop flags every `poll` steps (the reference does a
+    D2H sync + an H2D mask copy per token).
+  * NAR: 7 full-attention passes over packed [text | prompt | generated] rows with AdaLN stage
+    conditioning, argmax and the embedding accumulation fused on the device (valle.py:1115-1134).
+
+torch is used for allocation, streams and index bookkeeping; all arithmetic runs in
+libvalle_b200.so.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+NUM_AUDIO_TOKENS = 1024  # valle/models/macros.py:5
+
+
+@dataclass
+class EngineStats:
+    ar_steps: int = 0
+    ar_ms: float = 0.0
+    prefill_ms: float = 0.0
+    nar_ms: float = 0.0
+
+
+class _ArBuffers:
+    """Persistent device state for the AR loop at one (B, cache_cap, tok_stride) shape, plus the
+    captured CUDA graph of one decode step."""
+
+    def __init__(self, eng: "ValleEngine", B: int, cap: int, tok_stride: int):
+        dev, d = eng.device, eng.d
+        nd = eng.ar
+        self.B, self.cap, self.tok_stride = B, cap, tok_stride
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.text_len = torch.zeros(B, **i32)
+        self.prompt_len = torch.zeros(B, **i32)
+        self.max_new = torch.zeros(B, **i32)
+        self.n_gen = torch.zeros(B, **i32)
+        self.finished = torch.zeros(B, **i32)
+        self.tokens = torch.zeros((B, tok_stride), **i32)
+        self.x_cur = torch.zeros((B, d), dtype=torch.float32, device=dev)
+        self.ldl = (eng.n_vocab + 3) // 4 * 4
+        self.logits = torch.zeros((B, self.ldl), dtype=torch.float32, device=dev)
+        self.kcache = torch.zeros((nd.n_layer, B, nd.H, cap, 64), dtype=eng.dtype, device=dev)
+        self.vcache = torch.zeros_like(self.kcache)
+        st = L.ArState()
+        st.B, st.tok_stride = B, tok_stride
+        st.text_len, st.prompt_len, st.max_new = self.text_len.data_ptr(), self.prompt_len.data_ptr(), self.max_new.data_ptr()
+        st.n_gen, st.finished, st.tokens = self.n_gen.data_ptr(), self.finished.data_ptr(), self.tokens.data_ptr()
+        st.x_cur, st.logits = self.x_cur.data_ptr(), self.logits.data_ptr()
+        st.kcache, st.vcache = self.kcache.data_ptr(), self.vcache.data_ptr()
+        st.cache_layer_stride, st.cache_seq_stride, st.cache_cap = self.kcache.stride(0), self.kcache.stride(1), cap
+        self.st = st
+        nbytes = eng.lib.vb_ar_step_workspace(C.byref(nd.desc), B, cap)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+
+class ValleEngine:
+    def __init__(self, model, dtype: torch.dtype = torch.float32, use_cuda_graph: bool = True):
+        self.lib = L.load()
+        self.model = model
+        self.dtype = dtype
+        self.use_cuda_graph = use_cuda_graph
+        p = model.ar_predict_layer.weight
+        if not p.is_cuda:
+            raise L.VbError("valle_b200: move the model to a CUDA device first (no CPU fallback)")
+        self.device = p.device
+        self.d = p.shape[1]
+        self.n_vocab = p.shape[0]
+        self.Q = model.num_quantizers
+        self.prefix_mode = model.prefix_mode
+        self.stats = EngineStats()
+        self.quiet = False
+        self._bufs: Dict[Tuple[int, int, int], _ArBuffers] = {}
+        self._ada_cache = None
+        self._sig = None
+        self._refresh()
+
+    # ---- weights -----------------------------------------------------------------------
+    def _signature(self):
+        return tuple((q.data_ptr(), q._version) for q in self.model.parameters())
+
+    def _refresh(self):
+        sig = self._signature()
+        if sig == self._sig:
+            return
+        m = self.model
+        self._sig = sig
+        self.ar = m.ar_decoder.native(self.dtype)
+        self.nar = m.nar_decoder.native(self.dtype) if self.Q > 1 else None
+        cast = (lambda t: t.detach().to(self.dtype).contiguous()) if self.dtype != torch.float32 \
+            else (lambda t: t.detach())
+        self.ar_predict_w = cast(m.ar_predict_layer.weight)
+        self.nar_predict_w = [cast(l.weight) for l in m.nar_predict_layers] if self.Q > 1 else []
+        self._ada_cache = None
+        self._bufs.clear()  # graphs hold stale weight pointers
+
+    def _pe(self, module, n: int) -> torch.Tensor:
+        return module.table(n, self.device)
+
+    def _ada_tables(self) -> List[torch.Tensor]:
+        if self._ada_cache is None:
+            self._ada_cache = [self.nar.ada_table(e.weight) for e in self.model.nar_stage_embeddings]
+        return self._ada_cache
+
+    def _head(self, pe: torch.Tensor, greedy: bool) -> L.ArHead:
+        m = self.model
+        h = L.ArHead()
+        h.predict_w = self.ar_predict_w.data_ptr()
+        h.n_vocab, h.eos_id = self.n_vocab, NUM_AUDIO_TOKENS
+        h.audio_emb = m.ar_audio_embedding.weight.detach().data_ptr()
+        h.alpha = m.ar_audio_position.alpha.detach().data_ptr()
+        h.pe, h.pe_rows = pe.data_ptr(), pe.shape[0]
+        h.greedy = int(greedy)
+        return h
+
+    def _buffers(self, B: int, cap: int, tok_stride: int) -> _ArBuffers:
+        key = (B, cap, tok_stride)
+        b = self._bufs.get(key)
+        if b is None:
+            if len(self._bufs) > 4:
+                self._bufs.clear()
+            b = _ArBuffers(self, B, cap, tok_stride)
+            self._bufs[key] = b
+        return b
+
+    # ---- public API ----------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, texts: Sequence[torch.Tensor], prompts: Sequence[torch.Tensor],
+                 enroll_lens: Optional[Sequence[int]] = None, top_k: int = 1, temperature: float = 1.0,
+                 max_new_tokens: Optional[int] = None, poll: int = 32,
+                 return_device: bool = False) -> List[torch.Tensor]:
+        """texts[b]: int64 [S_b] phoneme ids; prompts[b]: int64 [Tp_b, Q] codec ids (host or device).
+        Returns codes[b]: int64 [Tgen_b, Q] -- per utterance exactly what VALLE.inference returns."""
+        self._refresh()
+        m, dev, d, Q = self.model, self.device, self.d, self.Q
+        B = len(texts)
+        assert B == len(prompts) and B >= 1
+        S = [int(t.numel()) for t in texts]
+        Tp = [int(p.shape[0]) for p in prompts]
+        assert all(s > 0 for s in S) and all(p.shape[1] == Q for p in prompts)
+        cap_new = [16 * s for s in S]  # valle.py:1047: stop when n_new > 16 * S
+        if max_new_tokens is not None:
+            cap_new = [min(c, max_new_tokens - 1) for c in cap_new]
+        tok_stride = (max(cap_new) + 2 + 7) // 8 * 8
+        cap = (max(S[b] + Tp[b] + cap_new[b] + 2 for b in range(B)) + 63) // 64 * 64
+        greedy = top_k == 1
+
+        # ---- host -> device (once per batch) ----
+        text_all = torch.cat([t.reshape(-1).to(torch.int64) for t in texts]).to(dev, non_blocking=True)
+        prm_all = torch.cat([p.to(torch.int64) for p in prompts]).contiguous().to(dev, non_blocking=True)
+        seq_len = [S[b] + Tp[b] for b in range(B)]
+        cu = [0]
+        for n in seq_len:
+            cu.append(cu[-1] + n)
+        M = cu[-1]
+        text_rows, text_pos, aud_rows, aud_pos = [], [], [], []
+        for b in range(B):
+            text_rows += range(cu[b], cu[b] + S[b])
+            text_pos += range(S[b])
+            aud_rows += range(cu[b] + S[b], cu[b + 1])
+            aud_pos += range(Tp[b])
+        meta = torch.tensor(cu + S + Tp + cap_new + text_rows + text_pos + aud_rows + aud_pos
+                            + [c - 1 for c in cu[1:]], dtype=torch.int32).to(dev, non_blocking=True)
+        o = 0
+        def take(n):
+            nonlocal o
+            v = meta[o:o + n]
+            o += n
+            return v
+        cu_d, S_d, Tp_d, capn_d = take(B + 1), take(B), take(B), take(B)
+        trow_d, tpos_d = take(sum(S)), take(sum(S))
+        arow_d, apos_d = take(sum(Tp)), take(sum(Tp))
+        last_d = take(B)
+
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        # ---- AR prefill (valle.py:995-997,1013-1016) ----
+        buf = self._buffers(B, cap, tok_stride)
+        buf.text_len.copy_(S_d)
+        buf.prompt_len.copy_(Tp_d)
+        buf.max_new.copy_(capn_d)
+        buf.n_gen.zero_()
+        buf.finished.zero_()
+        pe_t = self._pe(m.ar_text_position, max(S))
+        pe_a = self._pe(m.ar_audio_position, max(Tp) + max(cap_new) + 2)
+        x = torch.empty((M, d), dtype=torch.float32, device=dev)
+        self._embed_pe(text_all, 1, m.ar_text_embedding.weight, pe_t, m.ar_text_position.alpha, sum(S), x, trow_d, tpos_d)
+        self._embed_pe(prm_all, Q, m.ar_audio_embedding.weight, pe_a, m.ar_audio_position.alpha, sum(Tp), x, arow_d, apos_d)
+        self.ar.forward(x, cu_d, B, max(seq_len), L.VB_MASK_VALLE_AR, S_d, None, buf.kcache, buf.vcache, cap)
+        h_last = ops.gather_rows(x, last_d)
+        head = self._head(pe_a, greedy)
+        self._head_ref = head
+        L.check(self.lib.vb_ar_head_step(self.ar.handle, C.byref(head), h_last.data_ptr(), C.byref(buf.st),
+                                         0, 0, L.stream_ptr()), "vb_ar_head_step")
+        if not greedy:
+            self._sample_push(buf, head, top_k, temperature)
+        ev[1].record()
+
+        # ---- AR decode loop (valle.py:1012-1057) ----
+        max_steps = max(cap_new) + 1
+        steps = 0
+        while steps < max_steps:
+            n = min(poll, max_steps - steps)
+            for _ in range(n):
+                self._decode_step(buf, head, greedy, top_k, temperature)
+            steps += n
+            if bool((buf.finished != 0).all()):  # one D2H sync per `poll` steps
+                break
+        self.stats.ar_steps = steps
+        ev[2].record()
+        n_gen = buf.n_gen.cpu().tolist()
+        fin = buf.finished.cpu().tolist()
+        if any(f == 2 for f in fin):
+            raise SyntaxError("well trained model shouldn't reach here.")  # valle.py:1049-1052
+        if not self.quiet:
+            for b in range(B):
+                print(f"VALL-E EOS [{Tp[b]} -> {Tp[b] + n_gen[b]}]")  # valle.py:1054
+
+        # ---- NAR (valle.py:1059-1137) ----
+        Tg = n_gen
+        cu_g = [0]
+        for n in Tg:
+            cu_g.append(cu_g[-1] + n)
+        G = cu_g[-1]
+        codes = torch.empty((G, Q), dtype=torch.int64, device=dev)
+        src = torch.tensor([b * tok_stride + i for b in range(B) for i in range(Tg[b])], dtype=torch.int64, device=dev)
+        codes[:, 0] = buf.tokens.view(-1).index_select(0, src).to(torch.int64)
+        if Q > 1:
+            self._nar(texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, enroll_lens)
+        ev[3].record()
+        ev[3].synchronize()
+        self.stats.prefill_ms = ev[0].elapsed_time(ev[1])
+        self.stats.ar_ms = ev[1].elapsed_time(ev[2])
+        self.stats.nar_ms = ev[2].elapsed_time(ev[3])
+        if return_device:
+            return [codes[cu_g[b]:cu_g[b + 1]] for b in range(B)]
+        host = codes.cpu()
+        return [host[cu_g[b]:cu_g[b + 1]] for b in range(B)]
+
+    @torch.no_grad()
+    def continual(self, texts: Sequence[torch.Tensor], ys: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """VALLE.continual (valle.py:1139-1238): first-codebook codes are given, the 7 NAR stages
+        predict the rest; prefix = min(T // 2, 225) frames."""
+        self._refresh()
+        dev, Q = self.device, self.Q
+        B = len(texts)
+        S = [int(t.numel()) for t in texts]
+        T = [int(y.shape[0]) for y in ys]
+        Tp = [min(int(t * 0.5), 3 * 75) for t in T]
+        Tg = [T[b] - Tp[b] for b in range(B)]
+        text_all = torch.cat([t.reshape(-1).to(torch.int64) for t in texts]).to(dev)
+        prm_all = torch.cat([ys[b][:Tp[b]].to(torch.int64) for b in range(B)]).contiguous().to(dev)
+        cu_g = [0]
+        for n in Tg:
+            cu_g.append(cu_g[-1] + n)
+        codes = torch.empty((cu_g[-1], Q), dtype=torch.int64, device=dev)
+        codes[:, 0] = torch.cat([ys[b][Tp[b]:, 0].to(torch.int64) for b in range(B)]).to(dev)
+        self._nar(texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, None, trim_text=False)
+        return [codes[cu_g[b]:cu_g[b + 1]] for b in range(B)]
+
+    # ---- helpers ---------------------------------------------------------------------------
+    def _embed_pe(self, tokens, tok_stride, table, pe, alpha, n, x, rows, pos):
+        """x[rows[r]] = table[tokens[r*tok_stride]] + alpha * pe[pos[r]]  (embedding then position,
+        valle.py:995-997 / 1013-1015)."""
+        tmp = torch.empty((n, self.d), dtype=torch.float32, device=self.device)
+        ops.embed_sum(tokens, tok_stride, 0, [table.detach()], n, tmp)
+        ops.add_pe(tmp, pe, alpha.detach(), x, n, positions=pos, out_rows=rows)
+
+    def _decode_step(self, buf: _ArBuffers, head: L.ArHead, greedy: bool, top_k: int, temperature: float):
+        if greedy and self.use_cuda_graph:
+            key = (head.pe, head.predict_w, head.audio_emb)
+            if buf.graph is not None and buf.graph_key != key:
+                buf.graph = None
+            if buf.graph is None:
+                # warm-up launch (also sets function attributes), then capture the same call
+                self._launch_step(buf, head)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_step(buf, head)
+                buf.graph = g
+                buf.graph_head = head  # keep the struct alive
+                buf.graph_key = key
+                return  # the warm-up launch was this step
+            buf.graph.replay()
+            return
+        self._launch_step(buf, head)
+        if not greedy:
+            self._sample_push(buf, head, top_k, temperature)
+
+    def _launch_step(self, buf: _ArBuffers, head: L.ArHead):
+        L.check(self.lib.vb_ar_decode_step(self.ar.handle, C.byref(head), C.byref(buf.st), buf.ws.data_ptr(),
+                                           buf.ws.numel(), L.stream_ptr()), "vb_ar_decode_step")
+
+    def _sample_push(self, buf: _ArBuffers, head: L.ArHead, top_k: int, temperature: float):
+        """valle.py:1287-1302 topk_sampling with torch's own RNG stream (so a fixed torch seed gives
+        the reference's draws), then the stop rule + append on the device."""
+        logits = buf.logits[:, : self.n_vocab].clone()
+        if temperature != 1.0:
+            logits = logits / temperature
+        if top_k > 0:
+            k = min(max(top_k, 1), logits.size(-1))
+            kth = torch.topk(logits, k)[0][..., -1, None]
+            logits = logits.masked_fill(logits < kth, -float("inf"))
+        samp = torch.multinomial(torch.softmax(logits, dim=-1), num_samples=1).view(-1).contiguous()
+        L.check(self.lib.vb_ar_push_tokens(C.byref(head), C.byref(buf.st), samp.data_ptr(), self.d,
+                                           L.stream_ptr()), "vb_ar_push_tokens")
+
+    def _nar(self, texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, enroll_lens, trim_text: bool = True):
+        m, dev, d, Q = self.model, self.device, self.d, self.Q
+        B = len(S)
+        pm = self.prefix_mode
+        # text seen by the NAR decoder (valle.py:1068-1079)
+        if pm in (2, 4) and trim_text:
+            assert enroll_lens is not None
+            keep = []
+            off = 0
+            S2 = []
+            for b in range(B):
+                e = int(enroll_lens[b])
+                idx = [off] + list(range(off + e - 1, off + S[b]))
+                keep += idx
+                S2.append(len(idx))
+                off += S[b]
+            text_nar = text_all.index_select(0, torch.tensor(keep, dtype=torch.int64, device=dev))
+        else:
+            text_nar, S2 = text_all, list(S)
+        T = [Tp[b] + Tg[b] for b in range(B)]
+        Ltot = [S2[b] + T[b] for b in range(B)]
+        cu = [0]
+        for n in Ltot:
+            cu.append(cu[-1] + n)
+        M = cu[-1]
+        cu_t = [0]
+        for n in T:
+            cu_t.append(cu_t[-1] + n)
+        NT = cu_t[-1]
+        cu_p = [0]
+        for n in Tp:
+            cu_p.append(cu_p[-1] + n)
+        # index maps (host-built, one H2D)
+        trow, tpos, yrow, ypos, y_prompt_rows, y_gen_rows, tgt_rows = [], [], [], [], [], [], []
+        for b in range(B):
+            trow += range(cu[b], cu[b] + S2[b]); tpos += range(S2[b])
+            yrow += range(cu[b] + S2[b], cu[b + 1]); ypos += range(T[b])
+            y_prompt_rows += range(cu_t[b], cu_t[b] + Tp[b])
+            y_gen_rows += range(cu_t[b] + Tp[b], cu_t[b + 1])
+            tgt_rows += range(cu[b] + S2[b] + Tp[b], cu[b + 1])
+        meta = torch.tensor(cu + trow + tpos + yrow + ypos + y_prompt_rows + y_gen_rows + tgt_rows,
+                            dtype=torch.int32).to(dev)
+        o = 0
+        def take(n):
+            nonlocal o
+            v = meta[o:o + n]
+            o += n
+            return v
+        cu_d = take(B + 1)
+        trow_d, tpos_d = take(sum(S2)), take(sum(S2))
+        yrow_d, ypos_d = take(NT), take(NT)
+        yp_d, yg_d, tgt_d = take(sum(Tp)), take(sum(Tg)), take(sum(Tg))
+        G = sum(Tg)
+
+        emb = [e.weight.detach() for e in m.nar_audio_embeddings]
+        # y_emb = nar_audio_embeddings[0](y)  (valle.py:1064); rows packed [prompt_b | generated_b]
+        y_emb = torch.empty((NT, d), dtype=torch.float32, device=dev)
+        ops.embed_sum(prm_all, Q, 0, [emb[0]], sum(Tp), y_emb, out_rows=yp_d)
+        ops.embed_sum(codes, Q, 0, [emb[0]], G, y_emb, out_rows=yg_d)
+        if pm != 0:  # valle.py:1110-1113: prompt rows get all 8 codebooks up front, in order j=1..7
+            ops.embed_sum(prm_all[:, 1:], Q, 1, emb[1:Q], sum(Tp), y_emb, out_rows=yp_d, accumulate=True)
+        pe_t = self._pe(m.nar_text_position, max(S2))
+        pe_a = self._pe(m.nar_audio_position, max(T))
+        ada = self._ada_tables()
+        x = torch.empty((M, d), dtype=torch.float32, device=dev)
+        logits = torch.empty((G, NUM_AUDIO_TOKENS), dtype=torch.float32, device=dev)
+        for i in range(Q - 1):
+            # xy_pos = concat([nar_text_position(nar_text_embedding(text)), nar_audio_position(y_emb)])
+            self._embed_pe(text_nar, 1, m.nar_text_embedding.weight, pe_t, m.nar_text_position.alpha, sum(S2), x, trow_d, tpos_d)
+            ops.add_pe(y_emb, pe_a, m.nar_audio_position.alpha.detach(), x, NT, positions=ypos_d, out_rows=yrow_d)
+            self.nar.forward(x, cu_d, B, max(Ltot), L.VB_MASK_FULL, None, ada[i])
+            hn = self.nar.final_norm(x, ada[i], rows=tgt_d, out_dtype=self.dtype)
+            ops.linear(hn, self.nar_predict_w[i], None, L.VB_EPI_NONE, out=logits)
+            nxt = emb[i + 1] if i < Q - 2 else None
+            # samples -> codes[:, i+1]; y_emb[generated rows] += emb[i+1][samples]  (valle.py:1130-1134)
+            ops.nar_argmax_accumulate(logits, codes[:, i + 1], codes.stride(0), nxt,
+                                      y_emb if nxt is not None else None, yg_d)
+            if pm == 0 and i < Q - 2:  # valle.py:1104-1107
+                ops.embed_sum(prm_all[:, i + 1:], Q, 0, [emb[i + 1]], sum(Tp), y_emb, out_rows=yp_d, accumulate=True)

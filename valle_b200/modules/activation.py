@@ -1,0 +1,89 @@
+"""MultiheadAttention with the reference's constructor, parameter names and init order
+(valle/modules/activation.py:12-197); forward = sm_100a kernels (packed in-proj GEMM,
+ragged attention, out-proj GEMM).  Self-attention, batch_first, the masks of the VALL-E path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+from torch.nn.init import constant_, xavier_uniform_
+from torch.nn.modules.linear import NonDynamicallyQuantizableLinear
+from torch.nn.parameter import Parameter
+
+from .. import _lib as L
+from .. import ops
+
+
+class ValleARMask:
+    """Structured stand-in for the boolean [S+t, S+t] mask of valle.py:1010-1033: text rows see
+    all text, audio rows see text + causal audio.  The kernels evaluate the rule
+    kv_len(i) = max(S, i + 1) instead of reading a materialised mask."""
+
+    def __init__(self, text_lens: Tensor):
+        self.text_lens = text_lens
+
+
+class MultiheadAttention(nn.Module):
+    __constants__ = ["batch_first"]
+
+    def __init__(self, embed_dim, num_heads, dropout=0.0, bias=True, add_bias_kv=False, add_zero_attn=False,
+                 kdim=None, vdim=None, batch_first=False, linear1_cls=nn.Linear, linear2_cls=nn.Linear,
+                 device=None, dtype=None) -> None:
+        super().__init__()
+        if add_bias_kv or add_zero_attn or kdim not in (None, embed_dim) or vdim not in (None, embed_dim) \
+                or linear1_cls is not nn.Linear or linear2_cls is not nn.Linear or not bias:
+            raise NotImplementedError("valle_b200.MultiheadAttention: only the configuration VALLE "
+                                      "instantiates (packed in-proj, bias, nn.Linear) is built")
+        fk = {"device": device, "dtype": dtype}
+        self.embed_dim = embed_dim
+        self.kdim = self.vdim = embed_dim
+        self._qkv_same_embed_dim = True
+        self.num_heads = num_heads
+        self.dropout = dropout
+        self.batch_first = batch_first
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == embed_dim, "embed_dim must be divisible by num_heads"
+        self.bias_k = self.bias_v = None
+        self.in_proj_weight = Parameter(torch.empty((3 * embed_dim, embed_dim), **fk))
+        self.register_parameter("q_proj_weight", None)
+        self.register_parameter("k_proj_weight", None)
+        self.register_parameter("v_proj_weight", None)
+        self.in_proj_bias = Parameter(torch.empty(3 * embed_dim, **fk))
+        self.out_proj = NonDynamicallyQuantizableLinear(embed_dim, embed_dim, bias=True, **fk)
+        self.add_zero_attn = False
+        xavier_uniform_(self.in_proj_weight)
+        constant_(self.in_proj_bias, 0.0)
+        constant_(self.out_proj.bias, 0.0)
+
+    def forward(self, query: Tensor, key: Tensor, value: Tensor, key_padding_mask: Optional[Tensor] = None,
+                need_weights: bool = True, attn_mask=None, average_attn_weights: bool = True
+                ) -> Tuple[Tensor, Optional[Tensor]]:
+        if not (query is key and key is value):
+            raise NotImplementedError("valle_b200.MultiheadAttention: self-attention only")
+        if not self.batch_first or need_weights:
+            raise NotImplementedError("valle_b200.MultiheadAttention: batch_first=True, need_weights=False only")
+        B, Lq, d = query.shape
+        x = query.reshape(B * Lq, d).contiguous()
+        lens = torch.full((B,), Lq, dtype=torch.int32)
+        if key_padding_mask is not None:
+            lens = (~key_padding_mask).sum(dim=1).to(torch.int32).cpu()
+        # pack valid rows of every sequence
+        idx = torch.cat([torch.arange(int(n)) + b * Lq for b, n in enumerate(lens)]).to(x.device)
+        xp = x.index_select(0, idx)
+        cu = torch.zeros(B + 1, dtype=torch.int32)
+        cu[1:] = torch.cumsum(lens, 0)
+        cu = cu.to(x.device)
+        mode, tl = L.VB_MASK_FULL, None
+        if isinstance(attn_mask, ValleARMask):
+            mode, tl = L.VB_MASK_VALLE_AR, attn_mask.text_lens.to(device=x.device, dtype=torch.int32)
+        elif attn_mask is not None:
+            raise NotImplementedError("valle_b200.MultiheadAttention: pass attn_mask=ValleARMask(text_lens) "
+                                      "(structured form of valle.py:1010-1033) or None")
+        qkv = ops.linear(xp, self.in_proj_weight.detach(), self.in_proj_bias.detach())
+        o = ops.attention(qkv, cu, int(lens.max()), self.num_heads, mode, tl)
+        o = ops.linear(o, self.out_proj.weight.detach(), self.out_proj.bias.detach())
+        out = torch.zeros_like(x)
+        out.index_copy_(0, idx, o)
+        return out.view(B, Lq, d), None
