@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- audio tokens/sec of the VALL-E AR+NAR decode hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hot path over one batch of synthetic utterances per GPU:
+B utterances x (S=47 phonemes, 225-frame prompt) -> greedy AR decode to the reference's cap
+(16*S+1 = 753 frames, valle.py:1047) + 7 NAR passes -> B x 753 x 8 audio tokens.
+Weak scaling: every rank decodes its own B utterances (no data-path collective), then ONE
+all-gather of the code matrices.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+D_MODEL, N_HEAD, N_LAYER = 1024, 16, 12
+S_TEXT, T_PROMPT, N_Q = 47, 225, 8
+FRAMES = 16 * S_TEXT + 1  # 753: cap-terminated generation with random weights
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--frames", type=int, default=0, help="cap generated frames (0 = reference cap 16*S+1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm_gbs=j["hbm_gbs"], tflops=j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                    tflops_burst=j["bf16_tflops"], source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, tflops_burst=1590.0, source="B200_PROFILING.md fallback")
+
+
+# ----------------------------------------------------------------------------- synthetic workload
+def make_batch(B, seed, device=None, pinned=False):
+    g = torch.Generator().manual_seed(seed)
+    texts = [torch.randint(3, 100, (S_TEXT,), generator=g) for _ in range(B)]
+    prompts = [torch.randint(0, 1024, (T_PROMPT, N_Q), generator=g) for _ in range(B)]
+    if device is not None:
+        texts = [t.to(device) for t in texts]
+        prompts = [p.to(device) for p in prompts]
+    elif pinned:
+        texts = [t.pin_memory() for t in texts]
+        prompts = [p.pin_memory() for p in prompts]
+    return texts, prompts
+
+
+def build_model(device):
+    from valle_b200.models import VALLE
+    torch.manual_seed(0)
+    m = VALLE(D_MODEL, N_HEAD, N_LAYER, norm_first=True, add_prenet=False, prefix_mode=1,
+              share_embedding=True, nar_scale_factor=1.0, prepend_bos=False, num_quantizers=N_Q).eval()
+    return m.to(device)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- algorithmic work
+def ar_step_bytes(B, mean_len, esize):
+    """W + B * (KV_read(L) + KV_write); W = weights streamed once per step."""
+    per_layer = 12 * D_MODEL * D_MODEL
+    w = (N_LAYER * per_layer + 1025 * D_MODEL) * esize                # matrices + AR head
+    w += N_LAYER * 13 * D_MODEL * 4 + 2 * D_MODEL * 4                 # biases / LN affine (fp32)
+    kv = 2 * N_LAYER * D_MODEL * esize                                 # bytes per cached token (K+V)
+    return w + B * (kv * mean_len + kv)
+
+
+def nar_pass_flops(B, L, tgen):
+    M = B * L
+    return 2 * M * N_LAYER * 12 * D_MODEL * D_MODEL + N_LAYER * B * 4 * L * L * D_MODEL + 2 * B * tgen * D_MODEL * 1024
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def cpu_reference_sample(seconds, threads=None):
+    """The reference's own algorithm (oracle port: full recompute per token, batch 1, fp32) timed on
+    the host cores over a bounded sample: a few full-recompute AR iterations at increasing context +
+    one NAR pass, integrated over the 753-frame utterance."""
+    from oracle import valle_oracle as O
+    from valle_b200.models import VALLE
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    m = VALLE(D_MODEL, N_HEAD, N_LAYER, norm_first=True, add_prenet=False, prefix_mode=1, share_embedding=True,
+              nar_scale_factor=1.0, prepend_bos=False, num_quantizers=N_Q).eval()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    cfg = O.OracleConfig(D_MODEL, N_HEAD, N_LAYER, 1, N_Q)
+    g = torch.Generator().manual_seed(9)
+    x = torch.randint(3, 100, (1, S_TEXT), generator=g)
+    xe = O.pos_embed(sd["ar_text_embedding.word_embeddings.weight"][x], sd["ar_text_position.alpha"])
+
+    def ar_iter(t):  # one iteration of valle.py:1012-1057 with t audio tokens in context
+        yy = torch.randint(0, 1024, (1, t), generator=g)
+        ye = O.pos_embed(sd["ar_audio_embedding.word_embeddings.weight"][yy], sd["ar_audio_position.alpha"])
+        xy = torch.concat([xe, ye], dim=1)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            dec = O.encoder(sd, "ar_decoder", xy, cfg, blocked=O.ar_inference_mask(S_TEXT, t))
+            torch.nn.functional.linear(dec[:, -1], sd["ar_predict_layer.weight"])
+        return time.perf_counter() - t0
+
+    def nar_pass():
+        L = S_TEXT + T_PROMPT + FRAMES
+        xy = torch.randn(1, L, D_MODEL, generator=g)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            dec = O.encoder(sd, "nar_decoder", xy, cfg,
+                            stage_emb=sd["nar_stage_embeddings.0.word_embeddings.weight"])
+            torch.nn.functional.linear(dec[:, S_TEXT + T_PROMPT:], sd["nar_predict_layers.0.weight"])
+        return time.perf_counter() - t0
+
+    ctx = [T_PROMPT, T_PROMPT + FRAMES // 2, T_PROMPT + FRAMES - 1]
+    ar_iter(ctx[0])  # warm-up
+    t_budget = time.perf_counter()
+    times = {c: [] for c in ctx}
+    reps = 0
+    while reps < 1 or (time.perf_counter() - t_budget < seconds * 0.7 and reps < 5):
+        for c in ctx:
+            times[c].append(ar_iter(c))
+        reps += 1
+    tm = [min(times[c]) for c in ctx]
+    # piecewise-linear integral of the per-iteration time over the 753 iterations
+    half = FRAMES / 2.0
+    ar_total = half * (tm[0] + tm[1]) / 2 + half * (tm[1] + tm[2]) / 2
+    t_nar = nar_pass()
+    total = ar_total + 7 * t_nar
+    return dict(value=FRAMES * N_Q / total, seconds_per_utt=total, ar_seconds=ar_total, nar_pass_seconds=t_nar,
+                cores=threads,
+                sample=f"{reps}x3 full-recompute AR iterations at {ctx} audio tokens of context + 1 NAR pass "
+                       f"(L={S_TEXT + T_PROMPT + FRAMES}), B=1 fp32, integrated over {FRAMES} frames + 7 passes")
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    a = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch.distributed as dist
+    frames = a.frames or FRAMES
+
+    if a.impl == "reference":
+        # reference arm: the reference's CPU algorithm on the host cores (rank 0 only)
+        if world > 1:
+            dist.init_process_group("gloo")
+            if rank != 0:
+                dist.barrier()
+                dist.destroy_process_group()
+                return
+        vals = []
+        for i in range(a.warmup + a.steps):
+            r = cpu_reference_sample(max(4.0, min(a.cpu_seconds, 30.0)) if i >= a.warmup else 2.0)
+            if i >= a.warmup:
+                vals.append(r)
+        best = max(vals, key=lambda r: r["value"])
+        v = statistics.median([r["value"] for r in vals])
+        line = {"impl": "reference", "metric": "audio tokens/sec (AR+NAR d=1024/12L)", "value": v,
+                "unit": "tokens/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1000.0 * statistics.median([r["seconds_per_utt"] for r in vals]),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"AR+NAR infer, S={S_TEXT}, prompt {T_PROMPT} frames -> {FRAMES} frames x 8 "
+                                       "codebooks; reference algorithm (no KV cache, batch 1) on host cores"},
+                "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": best["cores"], "kind": "port",
+                                 "sample": best["sample"]},
+                "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from valle_b200 import dist as vdist
+    dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
+    esize = 2 if a.dtype == "bf16" else 4
+    model = build_model(dev)
+    eng = model.engine(dtype)
+    eng.quiet = True
+    B = a.batch
+    mnt = None if frames >= FRAMES else frames
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(texts, prompts, e2e):
+        if e2e:   # public API, pinned host inputs -> device, codes -> host
+            codes = model.inference_batch(texts, prompts, top_k=1, dtype=dtype, max_new_tokens=mnt)
+            if world > 1:
+                codes = vdist.gather_codes(codes, N_Q, dev)
+            return codes
+        codes = eng.generate(texts, prompts, top_k=1, max_new_tokens=mnt, return_device=True)
+        if world > 1:
+            codes = vdist.gather_codes(codes, N_Q, dev)
+        return codes
+
+    def timed(e2e, steps, warmup):
+        batches = [make_batch(B, 1000 * rank + i, None if e2e else dev, pinned=e2e) for i in range(2)]
+        for i in range(warmup):
+            one_step(*batches[i % 2], e2e)
+        barrier()
+        n0 = eng.kernel_launches()
+        st = []
+        ar_ms = nar_ms = pre_ms = 0.0
+        t_wall = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            codes = one_step(*batches[i % 2], e2e)
+            assert len(codes) == B * world
+            ar_ms += eng.stats.ar_ms; nar_ms += eng.stats.nar_ms; pre_ms += eng.stats.prefill_ms
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        wall = (time.perf_counter() - t_wall) * 1000.0
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return dict(ms=float(t.item()), wall_ms=wall, launches=eng.kernel_launches() - n0,
+                    ar_ms=ar_ms, nar_ms=nar_ms, prefill_ms=pre_ms, steps=eng.stats.ar_steps)
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    r = timed(False, a.steps, a.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    re = timed(True, a.steps, max(1, min(a.warmup, 1)))
+
+    tokens_step = B * frames * N_Q                     # per GPU per step
+    value = world * tokens_step * a.steps / (r["ms"] / 1000.0)
+    e2e_value = world * tokens_step * a.steps / (re["ms"] / 1000.0)
+    h2d = B * (S_TEXT + T_PROMPT * N_Q) * 8 + 4 * B * (4 + 2 * (S_TEXT + T_PROMPT) + 1)
+    d2h = B * frames * N_Q * 8 + 8 * B
+
+    pk = peaks()
+    mean_len = S_TEXT + T_PROMPT + frames / 2.0
+    ar_bytes = ar_step_bytes(B, mean_len, esize)
+    ar_step_s = (r["ar_ms"] / a.steps) / 1000.0 / max(1, r["steps"])
+    ach = ar_bytes / ar_step_s / 1e9
+    nar_fl = 7 * nar_pass_flops(B, S_TEXT + T_PROMPT + frames, frames)
+    nar_s = (r["nar_ms"] / a.steps) / 1000.0
+    line = {
+        "metric": "audio tokens/sec (AR+NAR d=1024/12L)", "value": value, "unit": "tokens/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms"] / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": f"e2e AR+NAR infer: {B} utterances/GPU x (S={S_TEXT}, {T_PROMPT}-frame prompt) -> "
+                               f"{frames} frames x {N_Q} codebooks, greedy, d={D_MODEL}/{N_HEAD}h/{N_LAYER}L",
+                   "batch_per_gpu": B, "parallelism": f"dp{world} (independent utterances, one final all-gather)",
+                   "l2": "working set (weights + KV cache > 1 GB) exceeds the 126 MB L2; inputs alternate between 2 batches"},
+        "gpu_launches": r["launches"],
+        "phase_ms_per_step": {"prefill": r["prefill_ms"] / a.steps, "ar": r["ar_ms"] / a.steps,
+                              "nar": r["nar_ms"] / a.steps, "ar_decode_steps": r["steps"]},
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": re["ms"] / a.steps},
+        "roofline": {"kernel": "AR decode step (CUDA graph of the per-layer LN+GEMV / KV-cache attention kernels)",
+                     "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                     "algorithmic_bytes_per_launch": ar_bytes, "launch_seconds": ar_step_s},
+        "roofline_nar": {"kernel": "7 NAR passes (QKV/out/FFN GEMMs + attention + heads)", "bound": "tensor",
+                         "achieved": nar_fl / nar_s / 1e12 if nar_s > 0 else None, "peak": pk["tflops"],
+                         "unit": "TFLOP/s", "frac": (nar_fl / nar_s / 1e12 / pk["tflops"]) if nar_s > 0 else None},
+        "clocks": clk,
+    }
+    if rank == 0 and a.gpus == 1 and not a.no_latency:
+        # BASELINE.json configs[1]: batch-1 greedy AR decode latency (p50 over 3 utterances)
+        lat, ar1 = [], []
+        t1, p1 = make_batch(1, 77, dev)
+        eng.generate(t1, p1, top_k=1, max_new_tokens=mnt, return_device=True)
+        for i in range(3):
+            t1, p1 = make_batch(1, 78 + i, dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            eng.generate(t1, p1, top_k=1, max_new_tokens=mnt, return_device=True)
+            torch.cuda.synchronize()
+            lat.append((time.perf_counter() - t0) * 1000.0)
+            ar1.append(eng.stats.ar_ms / max(1, eng.stats.ar_steps))
+        b1 = ar_step_bytes(1, mean_len, esize)
+        s1 = statistics.median(ar1) / 1000.0
+        line["p50_utt_latency_ms"] = statistics.median(lat)
+        line["roofline_b1"] = {"kernel": "AR decode step, batch 1", "bound": "hbm", "achieved": b1 / s1 / 1e9,
+                               "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": b1 / s1 / 1e9 / pk["hbm_gbs"],
+                               "ar_tokens_per_s": 1.0 / s1}
+    if rank == 0 and a.gpus == 1 and not a.no_cpu_baseline:
+        cb = cpu_reference_sample(a.cpu_seconds)
+        line["cpu_baseline"] = {"value": cb["value"], "unit": "tokens/s", "cores": cb["cores"], "kind": "port",
+                                "sample": cb["sample"]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

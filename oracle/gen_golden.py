@@ -32,7 +32,7 @@ def build_reference(ref, d, h, l, pm, seed):
 
 
 def checksums(sd):
-    return {k: torch.stack([v.double().sum(), v.double().abs().sum()]) for k, v in sd.items()}
+    return O.weight_checksums(sd)
 
 
 def make_inputs(gen, S, Tp):

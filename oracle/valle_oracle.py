@@ -22,7 +22,7 @@ PINNING: the reference's own tests hold no golden vectors for this path
 (valle/tests/valle_test.py is unseeded smoke testing).  The
 oracle is therefore pinned against *outputs of the reference itself run in the
 build container* (`oracle/ref_loader.py` exec's the unmodified files):
-`tests/test_oracle_vs_reference.py` compares every function here with the real
+`tests/test_oracle.py` compares every function here with the real
 classes whenever /root/reference is mounted, and `oracle/gen_golden.py` writes
 reference-generated fixtures to `tests/golden/` that travel to the GPU box.
 """
@@ -362,6 +362,18 @@ def ar_decode_kv(sd, cfg: OracleConfig, x, x_lens, y, max_new_tokens=None,
 # --------------------------------------------------------------------------
 # VALLE.forward (training loss) -- restated for the "training forward" row
 # --------------------------------------------------------------------------
+def weight_checksums(sd) -> Dict[str, torch.Tensor]:
+    """Order-independent exact fingerprint of every tensor: int64 sums over the raw fp32 bit
+    patterns (plain and position-weighted).  Integer arithmetic, so it does not depend on the
+    host's vector width -- a float64 sum does."""
+    out = {}
+    for k, v in sd.items():
+        bits = v.detach().cpu().contiguous().view(-1).view(torch.int32).to(torch.int64)
+        w = (torch.arange(bits.numel(), dtype=torch.int64) % 251) + 1
+        out[k] = torch.stack([bits.sum(), (bits * w).sum()])
+    return out
+
+
 def make_pad_mask(lengths: torch.Tensor, max_len: int = 0) -> torch.Tensor:
     """icefall.utils.make_pad_mask as called at valle.py:804-805."""
     max_len = max(max_len, int(lengths.max()))

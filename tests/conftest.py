@@ -32,11 +32,11 @@ def build_model(cfg, seed, device="cpu"):
 
 def assert_checksums(model, ck):
     import torch
-    sd = model.state_dict()
-    assert list(sd.keys()) == list(ck.keys())
-    for k, v in sd.items():
-        got = torch.stack([v.double().sum(), v.double().abs().sum()]).cpu()
-        assert torch.equal(got, ck[k]), f"weights differ from the reference init at {k}"
+    from oracle.valle_oracle import weight_checksums
+    got = weight_checksums(model.state_dict())
+    assert list(got.keys()) == list(ck.keys())
+    for k in got:
+        assert torch.equal(got[k], ck[k]), f"weights differ from the reference init at {k}"
 
 
 @pytest.fixture(scope="session")

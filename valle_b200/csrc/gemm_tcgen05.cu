@@ -1,11 +1,402 @@
-// placeholder until the tcgen05/TMEM GEMM lands (next commit)
+// bf16 GEMM on the 5th-generation tensor cores (sm_100a): C[M,N] = epi(A[M,K] W[N,K]^T + bias).
+//
+// Hand-written tcgen05 / TMEM / TMA kernel for the dense QKV / out-proj / FFN / head projections
+// of the NAR passes, the AR prefill and the training forward (F.linear at
+// valle/modules/activation.py:408, valle/modules/transformer.py:332-334, valle/models/valle.py:1128).
+//
+// Structure (persistent, one CTA per SM, 256 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2D loads of a 128 x 64 A box and a BN x 64 W box
+//               (both K-major, 128-byte swizzle) into a kStages-deep shared-memory ring, mbarrier
+//               complete_tx signalling.
+//   warp 1      MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//               (M=128, N=BN, K=16) x 4 per stage, accumulating fp32 in TMEM; tcgen05.commit frees
+//               the smem stage and, after the last k-block, publishes the accumulator.
+//   warp 2      TMEM allocator (2 accumulator buffers of BN columns -> epilogue of tile i overlaps
+//               the MMAs of tile i+1).
+//   warps 4-7   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, + bias, ReLU / residual,
+//               convert, 16-byte global stores.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 #include "kernels.cuh"
+
 namespace vb {
-bool tcgen05_gemm_supported(int64_t, int, int, int64_t, int64_t) { return false; }
-int launch_gemm_tcgen05(const bf16 *, int64_t, const bf16 *, const float *, void *, int, int64_t, int64_t, int,
-                        int, int, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
-  return VB_ERR_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 256;
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;
+  static constexpr int kABytes = BM * BK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * BK * 2;  // 32 KB / 16 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN;     // 512 / 256: power of two >= 32
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, bf16 x bf16 -> f32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (ignored for swizzled K-major, 1)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both,
+// N >> 3 @17, M >> 4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, int kEpi, typename TC>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const float *__restrict__ bias, TC *__restrict__ C, int64_t ldc, int M, int N, int K) {
+  using cfg = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzled tiles
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *tiles = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + cfg::kStages * cfg::kStageBytes);
+  uint64_t *full_bar = bars;                       // [kStages]
+  uint64_t *empty_bar = bars + cfg::kStages;       // [kStages]
+  uint64_t *tmem_full = bars + 2 * cfg::kStages;   // [2]
+  uint64_t *tmem_empty = tmem_full + 2;            // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = N / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = K / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(cfg::kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t *a_dst = tiles + stage * cfg::kStageBytes;
+          uint8_t *b_dst = a_dst + cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], cfg::kStageBytes);
+          tma_load_2d(&tmap_a, &full_bar[stage], a_dst, kb * BK, m_blk * BM);
+          tma_load_2d(&tmap_b, &full_bar[stage], b_dst, kb * BK, n_blk * BN);
+          if (++stage == cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + stage * cfg::kStageBytes);
+          const uint32_t b_addr = a_addr + cfg::kABytes;
+          const uint64_t adesc = make_smem_desc(a_addr);
+          const uint64_t bdesc = make_smem_desc(b_addr);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance along K inside the 128-byte swizzle atom: +32 bytes (>>4 = 2) per UMMA_K
+            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          tcgen05_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          if (++stage == cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tcgen05_commit(&tmem_full[acc]);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue =====
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = m_blk * BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      TC *crow = C + (int64_t)(row_ok ? row : 0) * ldc + n_blk * BN;
+      const float *brow = bias ? bias + n_blk * BN : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = __uint_as_float(r[i]);
+          if (brow) v[i] += __ldg(brow + c0 + i);
+          if constexpr (kEpi == VB_EPI_RELU) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (row_ok) {
+          if constexpr (sizeof(TC) == 4) {
+            float4 *dst = reinterpret_cast<float4 *>(crow + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              if constexpr (kEpi == VB_EPI_RESIDUAL) {
+                const float4 old = dst[i];
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              dst[i] = o;
+            }
+          } else {
+            uint4 *dst = reinterpret_cast<uint4 *>(crow + c0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+              uint4 o;
+              o.x = *reinterpret_cast<uint32_t *>(&p0);
+              o.y = *reinterpret_cast<uint32_t *>(&p1);
+              o.z = *reinterpret_cast<uint32_t *>(&p2);
+              o.w = *reinterpret_cast<uint32_t *>(&p3);
+              dst[i] = o;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(cfg::kTmemCols));
+  }
+}
+
+// ---- host: tensor maps -----------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// row-major [rows, K] bf16 matrix with leading dimension ld (elements); box = [box_rows, 64]
+static int make_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int K, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("tcgen05 gemm: cuTensorMapEncodeTiled entry point unavailable");
+    return VB_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tcgen05 gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld K=%d ld=%lld", (int)r, (long long)rows, K,
+              (long long)ld);
+    return VB_ERR_CUDA;
+  }
+  return VB_OK;
+}
+
+template <int BN, int kEpi, typename TC>
+static int launch_t(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, TC *C, int64_t ldc, int M,
+                    int N, int K, cudaStream_t s) {
+  using cfg = Cfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, kEpi, TC>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kThreads, cfg::kSmemBytes, s>>>(ta, tb, bias, C, ldc, M, N, K);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+template <int BN>
+static int launch_bn(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, void *C, int c_dtype,
+                     int64_t ldc, int M, int N, int K, int epi, cudaStream_t s) {
+  if (epi == VB_EPI_RESIDUAL) return launch_t<BN, VB_EPI_RESIDUAL, float>(ta, tb, bias, (float *)C, ldc, M, N, K, s);
+  if (epi == VB_EPI_RELU) {
+    if (c_dtype == VB_BF16) return launch_t<BN, VB_EPI_RELU, bf16>(ta, tb, bias, (bf16 *)C, ldc, M, N, K, s);
+    return launch_t<BN, VB_EPI_RELU, float>(ta, tb, bias, (float *)C, ldc, M, N, K, s);
+  }
+  if (c_dtype == VB_BF16) return launch_t<BN, VB_EPI_NONE, bf16>(ta, tb, bias, (bf16 *)C, ldc, M, N, K, s);
+  return launch_t<BN, VB_EPI_NONE, float>(ta, tb, bias, (float *)C, ldc, M, N, K, s);
+}
+
+}  // namespace tc
+
+bool tcgen05_gemm_supported(int64_t M, int N, int K, int64_t lda, int64_t ldc) {
+  return M >= 1 && M < (1LL << 31) && N % 128 == 0 && K % tc::BK == 0 && lda % 8 == 0 && ldc % 8 == 0 &&
+         getenv("VB_DISABLE_TCGEN05") == nullptr;
+}
+
+int launch_gemm_tcgen05(const bf16 *A, int64_t lda, const bf16 *W, const float *bias, void *C, int c_dtype,
+                        int64_t ldc, int64_t M, int N, int K, int epi, cudaStream_t s) {
+  VB_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+               "tcgen05 gemm: operands must be 16-byte aligned");
+  const int m_tiles = (int)((M + tc::BM - 1) / tc::BM);
+  const bool wide = (N % 256 == 0) && (m_tiles * (N / 256) >= sm_count());
+  const int BN = wide ? 256 : 128;
+  CUtensorMap ta, tb;
+  VB_TRY(tc::make_tmap(&ta, A, M, K, lda, tc::BM));
+  VB_TRY(tc::make_tmap(&tb, W, N, K, K, BN));
+  if (BN == 256) return tc::launch_bn<256>(ta, tb, bias, C, c_dtype, ldc, (int)M, N, K, epi, s);
+  return tc::launch_bn<128>(ta, tb, bias, C, c_dtype, ldc, (int)M, N, K, epi, s);
+}
+
 }  // namespace vb

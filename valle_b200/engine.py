@@ -87,6 +87,8 @@ class ValleEngine:
         self.prefix_mode = model.prefix_mode
         self.stats = EngineStats()
         self.quiet = False
+        self.replayed_launches = 0   # kernels executed through CUDA-graph replays
+        self.captured_launches = 0   # kernels recorded at capture time (counted by the library, not run)
         self._bufs: Dict[Tuple[int, int, int], _ArBuffers] = {}
         self._ada_cache = None
         self._sig = None
@@ -145,7 +147,7 @@ class ValleEngine:
     def generate(self, texts: Sequence[torch.Tensor], prompts: Sequence[torch.Tensor],
                  enroll_lens: Optional[Sequence[int]] = None, top_k: int = 1, temperature: float = 1.0,
                  max_new_tokens: Optional[int] = None, poll: int = 32,
-                 return_device: bool = False) -> List[torch.Tensor]:
+                 return_device: bool = False, trace: Optional[dict] = None) -> List[torch.Tensor]:
         """texts[b]: int64 [S_b] phoneme ids; prompts[b]: int64 [Tp_b, Q] codec ids (host or device).
         Returns codes[b]: int64 [Tgen_b, Q] -- per utterance exactly what VALLE.inference returns."""
         self._refresh()
@@ -211,6 +213,11 @@ class ValleEngine:
                                          0, 0, L.stream_ptr()), "vb_ar_head_step")
         if not greedy:
             self._sample_push(buf, head, top_k, temperature)
+        if trace is not None:  # test hook: AR logits of selected iterations (iteration 0 = prefill)
+            trace.setdefault("ar_logits", {})
+            if 0 in trace.get("steps", ()):
+                trace["ar_logits"][0] = buf.logits[:, : self.n_vocab].clone()
+            poll = 1
         ev[1].record()
 
         # ---- AR decode loop (valle.py:1012-1057) ----
@@ -221,6 +228,8 @@ class ValleEngine:
             for _ in range(n):
                 self._decode_step(buf, head, greedy, top_k, temperature)
             steps += n
+            if trace is not None and steps in trace.get("steps", ()):
+                trace["ar_logits"][steps] = buf.logits[:, : self.n_vocab].clone()
             if bool((buf.finished != 0).all()):  # one D2H sync per `poll` steps
                 break
         self.stats.ar_steps = steps
@@ -275,6 +284,10 @@ class ValleEngine:
         self._nar(texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, None, trim_text=False)
         return [codes[cu_g[b]:cu_g[b + 1]] for b in range(B)]
 
+    def kernel_launches(self) -> int:
+        """kernels of libvalle_b200.so executed so far by this process (direct + graph replays)."""
+        return int(self.lib.vb_launch_count()) - self.captured_launches + self.replayed_launches
+
     # ---- helpers ---------------------------------------------------------------------------
     def _embed_pe(self, tokens, tok_stride, table, pe, alpha, n, x, rows, pos):
         """x[rows[r]] = table[tokens[r*tok_stride]] + alpha * pe[pos[r]]  (embedding then position,
@@ -292,13 +305,17 @@ class ValleEngine:
                 # warm-up launch (also sets function attributes), then capture the same call
                 self._launch_step(buf, head)
                 g = torch.cuda.CUDAGraph()
+                n0 = self.lib.vb_launch_count()
                 with torch.cuda.graph(g):
                     self._launch_step(buf, head)
+                buf.graph_kernels = self.lib.vb_launch_count() - n0  # kernels inside one replay
+                self.captured_launches += buf.graph_kernels      # recorded, not executed
                 buf.graph = g
                 buf.graph_head = head  # keep the struct alive
                 buf.graph_key = key
                 return  # the warm-up launch was this step
             buf.graph.replay()
+            self.replayed_launches += buf.graph_kernels
             return
         self._launch_step(buf, head)
         if not greedy:
