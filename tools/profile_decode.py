@@ -1,0 +1,23 @@
+"""One engine.generate() call for profiling (ncu / launch lists): python tools/profile_decode.py B FRAMES [dtype] [nar]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+frames = int(sys.argv[2]) if len(sys.argv) > 2 else bench.FRAMES
+dtype = torch.float32 if (len(sys.argv) > 3 and sys.argv[3] == "fp32") else torch.bfloat16
+dev = torch.device("cuda", 0)
+model = bench.build_model(dev)
+if len(sys.argv) > 4 and sys.argv[4] == "ar_only":
+    model.num_quantizers_saved = model.num_quantizers
+eng = model.engine(dtype)
+eng.quiet = True
+texts, prompts = bench.make_batch(B, 0, dev)
+out = eng.generate(texts, prompts, top_k=1, max_new_tokens=None if frames >= bench.FRAMES else frames, return_device=True)
+torch.cuda.synchronize()
+print("frames", out[0].shape, "ar_ms", eng.stats.ar_ms, "steps", eng.stats.ar_steps, "nar_ms", eng.stats.nar_ms,
+      "prefill_ms", eng.stats.prefill_ms)

@@ -130,68 +130,118 @@ VB_API int vb_decoder_forward(vb_decoder_t dec, float *x, int64_t M, int B, cons
 // ------------------------------------------------------------------------------------------
 // AR decode
 // ------------------------------------------------------------------------------------------
+namespace {
+struct StepWs {
+  float *q, *att, *hb;
+  void *attn_ws;
+  bf16 *xn16, *att16, *hb16;
+  void *gemm_ws;
+  size_t gemm_ws_bytes;
+  size_t total;
+};
+StepWs carve_step_ws(const vb_decoder_desc &D, int B, int cache_cap, void *base) {
+  const size_t d = D.d_model, dff = D.d_ff;
+  StepWs w{};
+  char *p = (char *)base;
+  auto take = [&](size_t n) {
+    char *r = p;
+    p += align_up(n, 256);
+    return r;
+  };
+  w.q = (float *)take((size_t)B * d * 4);
+  w.att = (float *)take((size_t)B * d * 4);
+  w.hb = (float *)take((size_t)B * dff * 4);
+  w.attn_ws = take(attn_decode_workspace(B, D.n_head, (int)(d / D.n_head), cache_cap));
+  w.xn16 = (bf16 *)take((size_t)64 * d * 2);
+  w.att16 = (bf16 *)take((size_t)64 * d * 2);
+  w.hb16 = (bf16 *)take((size_t)64 * dff * 2);
+  w.gemm_ws_bytes = gemm_decode_workspace();
+  w.gemm_ws = take(w.gemm_ws_bytes);
+  w.total = (size_t)(p - (char *)base) + 256;
+  return w;
+}
+// tensor-core decode path: bf16 storage, more rows than the CUDA-core GEMV handles in one pass
+bool use_tc_decode(const vb_decoder_desc &D, int B) {
+  return D.wdtype == VB_BF16 && B > 8 && B <= 64 && getenv("VB_DECODE_SIMT") == nullptr;
+}
+}  // namespace
+
 VB_API size_t vb_ar_step_workspace(const vb_decoder_desc *desc, int B, int cache_cap) {
-  const size_t d = desc->d_model, dff = desc->d_ff;
-  size_t n = 0;
-  n += align_up((size_t)B * d * 4, 256);    // q
-  n += align_up((size_t)B * d * 4, 256);    // att
-  n += align_up((size_t)B * dff * 4, 256);  // ffn hidden
-  n += align_up(attn_decode_workspace(B, desc->n_head, (int)(d / desc->n_head), cache_cap), 256);
-  return n + 256;
+  return carve_step_ws(*desc, B, cache_cap, nullptr).total;
 }
 
 VB_API int vb_ar_head_step(vb_decoder_t dec, const vb_ar_head *head, const float *h, vb_ar_state *st,
-                               void *workspace, size_t workspace_bytes, vb_stream_t stream) {
-  (void)workspace;
-  (void)workspace_bytes;
+                           void *workspace, size_t workspace_bytes, vb_stream_t stream) {
   VB_CHECK_ARG(dec && head && h && st, "vb_ar_head_step: null argument");
   const vb_decoder_desc &D = dec->desc;
   cudaStream_t s = (cudaStream_t)stream;
   const int d = D.d_model;
   const int ldl = (head->n_vocab + 3) & ~3;
-  LnParams ln{D.final_norm_w, D.final_norm_b, nullptr, 1e-5f};
-  VB_TRY(launch_gemv(h, d, st->B, head->predict_w, D.wdtype, nullptr, head->n_vocab, d, st->logits, ldl,
-                     &ln, 0, nullptr, s));
+  if (use_tc_decode(D, st->B)) {
+    VB_CHECK_ARG(workspace && workspace_bytes >= vb_ar_step_workspace(&D, st->B, st->cache_cap),
+                 "vb_ar_head_step: workspace too small");
+    StepWs w = carve_step_ws(D, st->B, st->cache_cap, workspace);
+    VB_TRY(vb_layernorm(h, d, nullptr, st->B, d, D.final_norm_w, D.final_norm_b, nullptr, 1e-5f, w.xn16, VB_BF16,
+                        stream));
+    VB_TRY(launch_gemm_decode(w.xn16, st->B, d, (const bf16 *)head->predict_w, head->n_vocab, d, nullptr, DG_F32,
+                              st->logits, nullptr, ldl, nullptr, w.gemm_ws, w.gemm_ws_bytes, s));
+  } else {
+    LnParams ln{D.final_norm_w, D.final_norm_b, nullptr, 1e-5f};
+    VB_TRY(launch_gemv(h, d, st->B, head->predict_w, D.wdtype, nullptr, head->n_vocab, d, st->logits, ldl, &ln, 0,
+                       nullptr, s));
+  }
   if (head->greedy) VB_TRY(launch_ar_sample(st->logits, ldl, head, st, d, nullptr, s));
   return VB_OK;
 }
 
 VB_API int vb_ar_push_tokens(const vb_ar_head *head, vb_ar_state *st, const int64_t *sampled, int d,
-                                 vb_stream_t stream) {
+                             vb_stream_t stream) {
   VB_CHECK_ARG(head && st && sampled, "vb_ar_push_tokens: null argument");
   const int ldl = (head->n_vocab + 3) & ~3;
   return launch_ar_sample(st->logits, ldl, head, st, d, sampled, (cudaStream_t)stream);
 }
 
 VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_state *st, void *workspace,
-                                 size_t workspace_bytes, vb_stream_t stream) {
+                             size_t workspace_bytes, vb_stream_t stream) {
   VB_CHECK_ARG(dec && head && st, "vb_ar_decode_step: null argument");
   const vb_decoder_desc &D = dec->desc;
   VB_CHECK_ARG(workspace_bytes >= vb_ar_step_workspace(&D, st->B, st->cache_cap),
                "vb_ar_decode_step: workspace too small");
   cudaStream_t s = (cudaStream_t)stream;
-  const int d = D.d_model, dff = D.d_ff, B = st->B, dt = D.wdtype;
+  const int d = D.d_model, dff = D.d_ff, B = st->B, dt = D.wdtype, hd = d / D.n_head;
   const size_t ts = elem_size(dt);
-  char *ws = (char *)workspace;
-  float *q = (float *)ws;    ws += align_up((size_t)B * d * 4, 256);
-  float *att = (float *)ws;  ws += align_up((size_t)B * d * 4, 256);
-  float *hb = (float *)ws;   ws += align_up((size_t)B * dff * 4, 256);
-  void *aws = ws;
+  StepWs w = carve_step_ws(D, B, st->cache_cap, workspace);
   float *x = st->x_cur;
+  const bool tcp = use_tc_decode(D, B);
   for (int l = 0; l < D.n_layer; ++l) {
     const vb_layer_params &P = dec->layers[l];
     void *kc = (char *)st->kcache + (size_t)l * st->cache_layer_stride * ts;
     void *vc = (char *)st->vcache + (size_t)l * st->cache_layer_stride * ts;
-    LnParams ln1{P.norm1_w, P.norm1_b, nullptr, 1e-5f};
-    QkvScatter sc{d, d / D.n_head, q, kc, vc, st->cache_seq_stride, st->cache_cap,
-                  st->text_len, st->prompt_len, st->n_gen};
-    VB_TRY(launch_gemv(x, d, B, P.in_proj_w, dt, P.in_proj_b, 3 * d, d, nullptr, 0, &ln1, 3, &sc, s));
-    VB_TRY(launch_attn_decode(q, B, D.n_head, d / D.n_head, kc, vc, dt, st->cache_seq_stride, st->cache_cap,
-                              st->text_len, st->prompt_len, st->n_gen, att, aws, s));
-    VB_TRY(launch_gemv(att, d, B, P.out_proj_w, dt, P.out_proj_b, d, d, x, d, nullptr, 2, nullptr, s));
-    LnParams ln2{P.norm2_w, P.norm2_b, nullptr, 1e-5f};
-    VB_TRY(launch_gemv(x, d, B, P.lin1_w, dt, P.lin1_b, dff, d, hb, dff, &ln2, 1, nullptr, s));
-    VB_TRY(launch_gemv(hb, dff, B, P.lin2_w, dt, P.lin2_b, d, dff, x, d, nullptr, 2, nullptr, s));
+    QkvScatter sc{d, hd, w.q, kc, vc, st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen};
+    if (tcp) {
+      // LN -> bf16 rows -> swap-AB split-K tcgen05 projections with fused epilogues
+      VB_TRY(vb_layernorm(x, d, nullptr, B, d, P.norm1_w, P.norm1_b, nullptr, 1e-5f, w.xn16, VB_BF16, stream));
+      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)P.in_proj_w, 3 * d, d, P.in_proj_b, DG_QKV, nullptr,
+                                nullptr, d, &sc, w.gemm_ws, w.gemm_ws_bytes, s));
+      VB_TRY(launch_attn_decode(w.q, B, D.n_head, hd, kc, vc, dt, st->cache_seq_stride, st->cache_cap, st->text_len,
+                                st->prompt_len, st->n_gen, w.att, w.att16, w.attn_ws, s));
+      VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)P.out_proj_w, d, d, P.out_proj_b, DG_RESIDUAL, x,
+                                nullptr, d, nullptr, w.gemm_ws, w.gemm_ws_bytes, s));
+      VB_TRY(vb_layernorm(x, d, nullptr, B, d, P.norm2_w, P.norm2_b, nullptr, 1e-5f, w.xn16, VB_BF16, stream));
+      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)P.lin1_w, dff, d, P.lin1_b, DG_RELU_BF16, nullptr,
+                                w.hb16, dff, nullptr, w.gemm_ws, w.gemm_ws_bytes, s));
+      VB_TRY(launch_gemm_decode(w.hb16, B, dff, (const bf16 *)P.lin2_w, d, dff, P.lin2_b, DG_RESIDUAL, x, nullptr,
+                                d, nullptr, w.gemm_ws, w.gemm_ws_bytes, s));
+    } else {
+      LnParams ln1{P.norm1_w, P.norm1_b, nullptr, 1e-5f};
+      VB_TRY(launch_gemv(x, d, B, P.in_proj_w, dt, P.in_proj_b, 3 * d, d, nullptr, 0, &ln1, 3, &sc, s));
+      VB_TRY(launch_attn_decode(w.q, B, D.n_head, hd, kc, vc, dt, st->cache_seq_stride, st->cache_cap, st->text_len,
+                                st->prompt_len, st->n_gen, w.att, nullptr, w.attn_ws, s));
+      VB_TRY(launch_gemv(w.att, d, B, P.out_proj_w, dt, P.out_proj_b, d, d, x, d, nullptr, 2, nullptr, s));
+      LnParams ln2{P.norm2_w, P.norm2_b, nullptr, 1e-5f};
+      VB_TRY(launch_gemv(x, d, B, P.lin1_w, dt, P.lin1_b, dff, d, w.hb, dff, &ln2, 1, nullptr, s));
+      VB_TRY(launch_gemv(w.hb, dff, B, P.lin2_w, dt, P.lin2_b, d, dff, x, d, nullptr, 2, nullptr, s));
+    }
   }
-  return vb_ar_head_step(dec, head, x, st, nullptr, 0, stream);
+  return vb_ar_head_step(dec, head, x, st, workspace, workspace_bytes, stream);
 }

@@ -185,6 +185,9 @@ int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_
     VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, 256, smem, s>>>((const float *)qkv, n_head, cu_seqlens, text_lens, mask_mode, (float *)out,
                               (float *)kcache, (float *)vcache, cache_seq_stride, cache_cap);
+  } else if (dtype == VB_BF16 && getenv("VB_ATTN_SIMT") == nullptr) {
+    return launch_attention_mma((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, max_seqlen, mask_mode,
+                                (bf16 *)out, (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, s);
   } else if (dtype == VB_BF16) {
     auto k = attn_varlen_simt_kernel<bf16>;
     VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -223,8 +226,8 @@ __global__ void __launch_bounds__(128)
 attn_decode_kernel(const float *__restrict__ q, int n_head, const T *__restrict__ kcache,
                    const T *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
                    const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
-                   const int32_t *__restrict__ n_gen, float *__restrict__ out, float *__restrict__ part_o,
-                   float *__restrict__ part_ml, int nsplit) {
+                   const int32_t *__restrict__ n_gen, float *__restrict__ out, bf16 *__restrict__ out16,
+                   float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit) {
   __shared__ float sc[kDecMaxChunk];
   __shared__ __align__(16) float qs[HD];
   __shared__ float red[16][HD + 1];
@@ -315,6 +318,7 @@ attn_decode_kernel(const float *__restrict__ q, int n_head, const T *__restrict_
     for (int r = 0; r < 16; ++r) s += red[r][tid];
     if (nsplit == 1) {
       out[(int64_t)b * d + h * HD + tid] = s / l;
+      if (out16) out16[(int64_t)b * d + h * HD + tid] = __float2bfloat16_rn(s / l);
     } else {
       const int64_t pi = ((int64_t)b * n_head + h) * nsplit + sp;
       part_o[pi * HD + tid] = s;
@@ -328,7 +332,7 @@ attn_decode_kernel(const float *__restrict__ q, int n_head, const T *__restrict_
 
 __global__ void attn_decode_combine_kernel(const float *__restrict__ part_o,
                                            const float *__restrict__ part_ml, int n_head, int nsplit,
-                                           float *__restrict__ out) {
+                                           float *__restrict__ out, bf16 *__restrict__ out16) {
   const int h = blockIdx.x, b = blockIdx.y, e = threadIdx.x;
   const int64_t p0 = ((int64_t)b * n_head + h) * nsplit;
   float m = -CUDART_INF_F;
@@ -342,6 +346,7 @@ __global__ void attn_decode_combine_kernel(const float *__restrict__ part_o,
     o += part_o[(p0 + s) * HD + e] * w;
   }
   out[(int64_t)b * n_head * HD + h * HD + e] = o / l;
+  if (out16) out16[(int64_t)b * n_head * HD + h * HD + e] = __float2bfloat16_rn(o / l);
 }
 
 static int decode_nsplit(int B, int n_head, int cache_cap) {
@@ -360,7 +365,7 @@ size_t attn_decode_workspace(int B, int n_head, int head_dim, int cache_cap) {
 int launch_attn_decode(const float *q, int B, int n_head, int head_dim, const void *kcache,
                        const void *vcache, int dtype, int64_t cache_seq_stride, int cache_cap,
                        const int32_t *text_len, const int32_t *prompt_len, const int32_t *n_gen,
-                       float *out, void *workspace, cudaStream_t s) {
+                       float *out, void *out16, void *workspace, cudaStream_t s) {
   VB_CHECK_ARG(head_dim == HD, "attn_decode: head_dim=%d, only 64 is built", head_dim);
   const int ns = decode_nsplit(B, n_head, cache_cap);
   VB_CHECK_ARG((cache_cap + ns - 1) / ns + 16 <= kDecMaxChunk, "attn_decode: cache_cap %d too large", cache_cap);
@@ -370,14 +375,14 @@ int launch_attn_decode(const float *q, int B, int n_head, int head_dim, const vo
   if (dtype == VB_F32)
     attn_decode_kernel<float><<<grid, 128, 0, s>>>(q, n_head, (const float *)kcache, (const float *)vcache,
                                                    cache_seq_stride, cache_cap, text_len, prompt_len, n_gen,
-                                                   out, part_o, part_ml, ns);
+                                                   out, (bf16 *)out16, part_o, part_ml, ns);
   else
     attn_decode_kernel<bf16><<<grid, 128, 0, s>>>(q, n_head, (const bf16 *)kcache, (const bf16 *)vcache,
                                                   cache_seq_stride, cache_cap, text_len, prompt_len, n_gen,
-                                                  out, part_o, part_ml, ns);
+                                                  out, (bf16 *)out16, part_o, part_ml, ns);
   VB_LAUNCH_CHECK();
   if (ns > 1) {
-    attn_decode_combine_kernel<<<dim3(n_head, B), HD, 0, s>>>(part_o, part_ml, n_head, ns, out);
+    attn_decode_combine_kernel<<<dim3(n_head, B), HD, 0, s>>>(part_o, part_ml, n_head, ns, out, (bf16 *)out16);
     VB_LAUNCH_CHECK();
   }
   return VB_OK;

@@ -67,7 +67,7 @@ class _ArBuffers:
         st.cache_layer_stride, st.cache_seq_stride, st.cache_cap = self.kcache.stride(0), self.kcache.stride(1), cap
         self.st = st
         nbytes = eng.lib.vb_ar_step_workspace(C.byref(nd.desc), B, cap)
-        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
 
 
@@ -210,7 +210,7 @@ class ValleEngine:
         head = self._head(pe_a, greedy)
         self._head_ref = head
         L.check(self.lib.vb_ar_head_step(self.ar.handle, C.byref(head), h_last.data_ptr(), C.byref(buf.st),
-                                         0, 0, L.stream_ptr()), "vb_ar_head_step")
+                                         buf.ws.data_ptr(), buf.ws.numel(), L.stream_ptr()), "vb_ar_head_step")
         if not greedy:
             self._sample_push(buf, head, top_k, temperature)
         if trace is not None:  # test hook: AR logits of selected iterations (iteration 0 = prefill)
