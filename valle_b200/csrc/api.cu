@@ -160,15 +160,44 @@ StepWs carve_step_ws(const vb_decoder_desc &D, int B, int cache_cap, void *base)
   w.total = (size_t)(p - (char *)base) + 256;
   return w;
 }
-// tensor-core decode path: bf16 storage, more rows than the CUDA-core GEMV handles in one pass
+// tensor-core decode path: bf16 storage, up to 64 rows (one UMMA N tile)
 bool use_tc_decode(const vb_decoder_desc &D, int B) {
-  return D.wdtype == VB_BF16 && B > 8 && B <= 64 && getenv("VB_DECODE_SIMT") == nullptr;
+  return D.wdtype == VB_BF16 && B >= 1 && B <= 64 && getenv("VB_DECODE_SIMT") == nullptr;
 }
 }  // namespace
 
 VB_API size_t vb_ar_step_workspace(const vb_decoder_desc *desc, int B, int cache_cap) {
   return carve_step_ws(*desc, B, cache_cap, nullptr).total;
 }
+
+namespace {
+struct Pending {  // split-K partials of a projection whose bias/residual the next ln_reduce applies
+  const float *part = nullptr;
+  const float *bias = nullptr;
+  int splits = 0, ldp = 0;
+};
+bool use_pdl() { return getenv("VB_NO_PDL") == nullptr; }
+
+// final LayerNorm + ar_predict_layer + sampler on the tensor-core path
+int tc_head(vb_decoder *dec, const vb_ar_head *head, float *x, vb_ar_state *st, const StepWs &w, const Pending &pend,
+            cudaStream_t s) {
+  const vb_decoder_desc &D = dec->desc;
+  const int d = D.d_model, B = st->B;
+  const int ldl = (head->n_vocab + 3) & ~3;
+  const bool pdl = use_pdl();
+  VB_TRY(launch_ln_reduce(x, d, B, d, pend.part, pend.splits, pend.ldp, pend.bias, D.final_norm_w, D.final_norm_b,
+                          1e-5f, w.xn16, pdl, s));
+  int sp = 1, ldp = 0;
+  VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)head->predict_w, head->n_vocab, d, 0, nullptr, DG_F32,
+                            st->logits, nullptr, ldl, nullptr, (float *)w.gemm_ws, w.gemm_ws_bytes, &sp, &ldp, pdl, s));
+  if (head->greedy)
+    VB_TRY(launch_ar_sample(st->logits, ldl, sp > 1 ? (const float *)w.gemm_ws : nullptr, sp, ldp, head, st, d, nullptr,
+                            0, pdl, s));
+  else if (sp > 1)  // logits only (host-side sampling follows): just reduce the partials
+    VB_TRY(launch_ar_sample(st->logits, ldl, (const float *)w.gemm_ws, sp, ldp, head, st, d, nullptr, 1, pdl, s));
+  return VB_OK;
+}
+}  // namespace
 
 VB_API int vb_ar_head_step(vb_decoder_t dec, const vb_ar_head *head, const float *h, vb_ar_state *st,
                            void *workspace, size_t workspace_bytes, vb_stream_t stream) {
@@ -181,16 +210,12 @@ VB_API int vb_ar_head_step(vb_decoder_t dec, const vb_ar_head *head, const float
     VB_CHECK_ARG(workspace && workspace_bytes >= vb_ar_step_workspace(&D, st->B, st->cache_cap),
                  "vb_ar_head_step: workspace too small");
     StepWs w = carve_step_ws(D, st->B, st->cache_cap, workspace);
-    VB_TRY(vb_layernorm(h, d, nullptr, st->B, d, D.final_norm_w, D.final_norm_b, nullptr, 1e-5f, w.xn16, VB_BF16,
-                        stream));
-    VB_TRY(launch_gemm_decode(w.xn16, st->B, d, (const bf16 *)head->predict_w, head->n_vocab, d, nullptr, DG_F32,
-                              st->logits, nullptr, ldl, nullptr, w.gemm_ws, w.gemm_ws_bytes, s));
-  } else {
-    LnParams ln{D.final_norm_w, D.final_norm_b, nullptr, 1e-5f};
-    VB_TRY(launch_gemv(h, d, st->B, head->predict_w, D.wdtype, nullptr, head->n_vocab, d, st->logits, ldl, &ln, 0,
-                       nullptr, s));
+    return tc_head(dec, head, const_cast<float *>(h), st, w, Pending{}, s);
   }
-  if (head->greedy) VB_TRY(launch_ar_sample(st->logits, ldl, head, st, d, nullptr, s));
+  LnParams ln{D.final_norm_w, D.final_norm_b, nullptr, 1e-5f};
+  VB_TRY(launch_gemv(h, d, st->B, head->predict_w, D.wdtype, nullptr, head->n_vocab, d, st->logits, ldl, &ln, 0,
+                     nullptr, s));
+  if (head->greedy) VB_TRY(launch_ar_sample(st->logits, ldl, nullptr, 0, 0, head, st, d, nullptr, 0, false, s));
   return VB_OK;
 }
 
@@ -198,7 +223,7 @@ VB_API int vb_ar_push_tokens(const vb_ar_head *head, vb_ar_state *st, const int6
                              vb_stream_t stream) {
   VB_CHECK_ARG(head && st && sampled, "vb_ar_push_tokens: null argument");
   const int ldl = (head->n_vocab + 3) & ~3;
-  return launch_ar_sample(st->logits, ldl, head, st, d, sampled, (cudaStream_t)stream);
+  return launch_ar_sample(st->logits, ldl, nullptr, 0, 0, head, st, d, sampled, 0, false, (cudaStream_t)stream);
 }
 
 VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_state *st, void *workspace,
@@ -212,36 +237,55 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
   const size_t ts = elem_size(dt);
   StepWs w = carve_step_ws(D, B, st->cache_cap, workspace);
   float *x = st->x_cur;
-  const bool tcp = use_tc_decode(D, B);
+  if (use_tc_decode(D, B)) {
+    // bf16 tensor-core path: LayerNorm(+pending residual) -> swap-AB split-K tcgen05 projections whose
+    // partial sums are consumed by the next kernel in the chain (7 launches per layer, PDL-chained)
+    const bool pdl = use_pdl();
+    float *P = (float *)w.gemm_ws;
+    Pending pend;
+    for (int l = 0; l < D.n_layer; ++l) {
+      const vb_layer_params &L = dec->layers[l];
+      void *kc = (char *)st->kcache + (size_t)l * st->cache_layer_stride * ts;
+      void *vc = (char *)st->vcache + (size_t)l * st->cache_layer_stride * ts;
+      QkvScatter sc{d, hd, w.q, kc, vc, st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen};
+      VB_TRY(launch_ln_reduce(x, d, B, d, pend.part, pend.splits, pend.ldp, pend.bias, L.norm1_w, L.norm1_b, 1e-5f,
+                              w.xn16, pdl, s));
+      int s1 = 1, ldp1 = 0;
+      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.in_proj_w, 3 * d, d, 0, L.in_proj_b, DG_QKV, nullptr,
+                                nullptr, d, &sc, P, w.gemm_ws_bytes, &s1, &ldp1, pdl, s));
+      VB_TRY(launch_attn_decode(w.q, s1 > 1 ? P : nullptr, s1, ldp1, L.in_proj_b, B, D.n_head, hd, kc, vc, dt,
+                                st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen, w.att,
+                                w.att16, w.attn_ws, pdl, s));
+      int s2 = 1, ldp2 = 0;
+      VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)L.out_proj_w, d, d, 0, L.out_proj_b, DG_RESIDUAL, x,
+                                nullptr, d, nullptr, P, w.gemm_ws_bytes, &s2, &ldp2, pdl, s));
+      VB_TRY(launch_ln_reduce(x, d, B, d, s2 > 1 ? P : nullptr, s2, ldp2, L.out_proj_b, L.norm2_w, L.norm2_b, 1e-5f,
+                              w.xn16, pdl, s));
+      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.lin1_w, dff, d, 1, L.lin1_b, DG_RELU_BF16, nullptr,
+                                w.hb16, dff, nullptr, P, w.gemm_ws_bytes, nullptr, nullptr, pdl, s));
+      int s3 = 1, ldp3 = 0;
+      VB_TRY(launch_gemm_decode(w.hb16, B, dff, (const bf16 *)L.lin2_w, d, dff, 0, L.lin2_b, DG_RESIDUAL, x, nullptr,
+                                d, nullptr, P, w.gemm_ws_bytes, &s3, &ldp3, pdl, s));
+      pend = Pending{};
+      if (s3 > 1) {
+        pend.part = P; pend.bias = L.lin2_b; pend.splits = s3; pend.ldp = ldp3;
+      }
+    }
+    return tc_head(dec, head, x, st, w, pend, s);
+  }
   for (int l = 0; l < D.n_layer; ++l) {
     const vb_layer_params &P = dec->layers[l];
     void *kc = (char *)st->kcache + (size_t)l * st->cache_layer_stride * ts;
     void *vc = (char *)st->vcache + (size_t)l * st->cache_layer_stride * ts;
     QkvScatter sc{d, hd, w.q, kc, vc, st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen};
-    if (tcp) {
-      // LN -> bf16 rows -> swap-AB split-K tcgen05 projections with fused epilogues
-      VB_TRY(vb_layernorm(x, d, nullptr, B, d, P.norm1_w, P.norm1_b, nullptr, 1e-5f, w.xn16, VB_BF16, stream));
-      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)P.in_proj_w, 3 * d, d, P.in_proj_b, DG_QKV, nullptr,
-                                nullptr, d, &sc, w.gemm_ws, w.gemm_ws_bytes, s));
-      VB_TRY(launch_attn_decode(w.q, B, D.n_head, hd, kc, vc, dt, st->cache_seq_stride, st->cache_cap, st->text_len,
-                                st->prompt_len, st->n_gen, w.att, w.att16, w.attn_ws, s));
-      VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)P.out_proj_w, d, d, P.out_proj_b, DG_RESIDUAL, x,
-                                nullptr, d, nullptr, w.gemm_ws, w.gemm_ws_bytes, s));
-      VB_TRY(vb_layernorm(x, d, nullptr, B, d, P.norm2_w, P.norm2_b, nullptr, 1e-5f, w.xn16, VB_BF16, stream));
-      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)P.lin1_w, dff, d, P.lin1_b, DG_RELU_BF16, nullptr,
-                                w.hb16, dff, nullptr, w.gemm_ws, w.gemm_ws_bytes, s));
-      VB_TRY(launch_gemm_decode(w.hb16, B, dff, (const bf16 *)P.lin2_w, d, dff, P.lin2_b, DG_RESIDUAL, x, nullptr,
-                                d, nullptr, w.gemm_ws, w.gemm_ws_bytes, s));
-    } else {
-      LnParams ln1{P.norm1_w, P.norm1_b, nullptr, 1e-5f};
-      VB_TRY(launch_gemv(x, d, B, P.in_proj_w, dt, P.in_proj_b, 3 * d, d, nullptr, 0, &ln1, 3, &sc, s));
-      VB_TRY(launch_attn_decode(w.q, B, D.n_head, hd, kc, vc, dt, st->cache_seq_stride, st->cache_cap, st->text_len,
-                                st->prompt_len, st->n_gen, w.att, nullptr, w.attn_ws, s));
-      VB_TRY(launch_gemv(w.att, d, B, P.out_proj_w, dt, P.out_proj_b, d, d, x, d, nullptr, 2, nullptr, s));
-      LnParams ln2{P.norm2_w, P.norm2_b, nullptr, 1e-5f};
-      VB_TRY(launch_gemv(x, d, B, P.lin1_w, dt, P.lin1_b, dff, d, w.hb, dff, &ln2, 1, nullptr, s));
-      VB_TRY(launch_gemv(w.hb, dff, B, P.lin2_w, dt, P.lin2_b, d, dff, x, d, nullptr, 2, nullptr, s));
-    }
+    LnParams ln1{P.norm1_w, P.norm1_b, nullptr, 1e-5f};
+    VB_TRY(launch_gemv(x, d, B, P.in_proj_w, dt, P.in_proj_b, 3 * d, d, nullptr, 0, &ln1, 3, &sc, s));
+    VB_TRY(launch_attn_decode(w.q, nullptr, 0, 0, nullptr, B, D.n_head, hd, kc, vc, dt, st->cache_seq_stride,
+                              st->cache_cap, st->text_len, st->prompt_len, st->n_gen, w.att, nullptr, w.attn_ws, false, s));
+    VB_TRY(launch_gemv(w.att, d, B, P.out_proj_w, dt, P.out_proj_b, d, d, x, d, nullptr, 2, nullptr, s));
+    LnParams ln2{P.norm2_w, P.norm2_b, nullptr, 1e-5f};
+    VB_TRY(launch_gemv(x, d, B, P.lin1_w, dt, P.lin1_b, dff, d, w.hb, dff, &ln2, 1, nullptr, s));
+    VB_TRY(launch_gemv(w.hb, dff, B, P.lin2_w, dt, P.lin2_b, d, dff, x, d, nullptr, 2, nullptr, s));
   }
   return vb_ar_head_step(dec, head, x, st, workspace, workspace_bytes, stream);
 }

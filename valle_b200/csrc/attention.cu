@@ -221,28 +221,65 @@ template <> __device__ __forceinline__ void KvRow8<bf16>::load(const bf16 *p, fl
   v.unpack(f);
 }
 
+// Optional fused prologue: q/k/v of the CURRENT token arrive as split-K partials of the QKV
+// projection (gemm_decode.cu); the CTA sums them in fixed order, adds the bias, appends k/v to the
+// cache (split 0) and serves the new key/value from shared memory.
+struct QkvPartials {
+  const float *part;  // [splits][64][ldp] or nullptr
+  const float *bias;  // [3d]
+  int splits, ldp;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(128)
-attn_decode_kernel(const float *__restrict__ q, int n_head, const T *__restrict__ kcache,
-                   const T *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
+attn_decode_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *__restrict__ kcache,
+                   T *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
                    const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
                    const int32_t *__restrict__ n_gen, float *__restrict__ out, bf16 *__restrict__ out16,
                    float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit) {
   __shared__ float sc[kDecMaxChunk];
   __shared__ __align__(16) float qs[HD];
+  __shared__ __align__(16) float knew[HD];
+  __shared__ __align__(16) float vnew[HD];
   __shared__ float red[16][HD + 1];
   __shared__ float wred[8];
+  pdl_launch_dependents();
   const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = n_head * HD;
+  pdl_wait();
   int kv_len = text_len[b] + prompt_len[b] + n_gen[b];
   kv_len = max(1, min(kv_len, cache_cap));
+  const int pos = kv_len - 1;  // cache row of the current token
   const int chunk = ((kv_len + nsplit - 1) / nsplit + 15) & ~15;
   const int c0 = sp * chunk, c1 = min(kv_len, c0 + chunk);
   const int n = max(0, c1 - c0);
-  const T *kb = kcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
-  const T *vb_ = vcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
-  if (tid < HD) qs[tid] = q[(int64_t)b * d + h * HD + tid] * 0.125f;
+  T *kb = kcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
+  T *vb_ = vcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
+  const bool has_new = qp.part != nullptr;
+  if (tid < HD) {
+    if (has_new) {
+      float a[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int col = j * d + h * HD + tid;
+        const float *p = qp.part + (int64_t)b * qp.ldp + col;
+        float acc = p[0];
+        for (int s = 1; s < qp.splits; ++s) acc += p[(int64_t)s * 64 * qp.ldp];
+        a[j] = acc + qp.bias[col];
+      }
+      qs[tid] = a[0] * 0.125f;
+      const T k16 = from_f32<T>(a[1]), v16 = from_f32<T>(a[2]);
+      knew[tid] = to_f32(k16);  // exactly what later steps will read back from the cache
+      vnew[tid] = to_f32(v16);
+      if (sp == 0) {
+        kb[(int64_t)pos * HD + tid] = k16;
+        vb_[(int64_t)pos * HD + tid] = v16;
+      }
+    } else {
+      qs[tid] = q[(int64_t)b * d + h * HD + tid] * 0.125f;
+    }
+  }
   __syncthreads();
 
   // ---- scores: 8 lanes per key, 4 keys per warp-iteration, 16 keys per CTA-iteration ----
@@ -258,6 +295,10 @@ attn_decode_kernel(const float *__restrict__ q, int n_head, const T *__restrict_
       const int key = base + u * 16 + warp * 4 + g;
       const int kk = min(key, n - 1);
       KvRow8<T>::load(kb + (int64_t)(c0 + kk) * HD + j8, kf[u]);
+      if (has_new && c0 + kk == pos) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) kf[u][i] = knew[j8 + i];
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -303,6 +344,10 @@ attn_decode_kernel(const float *__restrict__ q, int n_head, const T *__restrict_
       const int kk = min(key, n - 1);
       pv[u] = key < n ? sc[kk] : 0.f;
       KvRow8<T>::load(vb_ + (int64_t)(c0 + kk) * HD + eg, vf[u]);
+      if (has_new && c0 + kk == pos) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vf[u][i] = vnew[eg + i];
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -333,6 +378,8 @@ attn_decode_kernel(const float *__restrict__ q, int n_head, const T *__restrict_
 __global__ void attn_decode_combine_kernel(const float *__restrict__ part_o,
                                            const float *__restrict__ part_ml, int n_head, int nsplit,
                                            float *__restrict__ out, bf16 *__restrict__ out16) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.x, b = blockIdx.y, e = threadIdx.x;
   const int64_t p0 = ((int64_t)b * n_head + h) * nsplit;
   float m = -CUDART_INF_F;
@@ -362,28 +409,30 @@ size_t attn_decode_workspace(int B, int n_head, int head_dim, int cache_cap) {
   return (size_t)B * n_head * ns * (head_dim + 2) * sizeof(float) + 256;
 }
 
-int launch_attn_decode(const float *q, int B, int n_head, int head_dim, const void *kcache,
-                       const void *vcache, int dtype, int64_t cache_seq_stride, int cache_cap,
-                       const int32_t *text_len, const int32_t *prompt_len, const int32_t *n_gen,
-                       float *out, void *out16, void *workspace, cudaStream_t s) {
+int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, int qkv_ldp, const float *qkv_bias,
+                       int B, int n_head, int head_dim, void *kcache, void *vcache, int dtype,
+                       int64_t cache_seq_stride, int cache_cap, const int32_t *text_len, const int32_t *prompt_len,
+                       const int32_t *n_gen, float *out, void *out16, void *workspace, bool pdl, cudaStream_t s) {
   VB_CHECK_ARG(head_dim == HD, "attn_decode: head_dim=%d, only 64 is built", head_dim);
   const int ns = decode_nsplit(B, n_head, cache_cap);
   VB_CHECK_ARG((cache_cap + ns - 1) / ns + 16 <= kDecMaxChunk, "attn_decode: cache_cap %d too large", cache_cap);
   float *part_o = (float *)workspace;
   float *part_ml = part_o + (size_t)B * n_head * ns * HD;
+  QkvPartials qp{qkv_part, qkv_bias, qkv_splits, qkv_ldp};
   dim3 grid(n_head, B, ns);
   if (dtype == VB_F32)
-    attn_decode_kernel<float><<<grid, 128, 0, s>>>(q, n_head, (const float *)kcache, (const float *)vcache,
-                                                   cache_seq_stride, cache_cap, text_len, prompt_len, n_gen,
-                                                   out, (bf16 *)out16, part_o, part_ml, ns);
+    VB_CUDA(launch_kernel(attn_decode_kernel<float>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (float *)kcache,
+                          (float *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
+                          (bf16 *)out16, part_o, part_ml, ns));
   else
-    attn_decode_kernel<bf16><<<grid, 128, 0, s>>>(q, n_head, (const bf16 *)kcache, (const bf16 *)vcache,
-                                                  cache_seq_stride, cache_cap, text_len, prompt_len, n_gen,
-                                                  out, (bf16 *)out16, part_o, part_ml, ns);
-  VB_LAUNCH_CHECK();
+    VB_CUDA(launch_kernel(attn_decode_kernel<bf16>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
+                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
+                          (bf16 *)out16, part_o, part_ml, ns));
+  count_launch();
   if (ns > 1) {
-    attn_decode_combine_kernel<<<dim3(n_head, B), HD, 0, s>>>(part_o, part_ml, n_head, ns, out, (bf16 *)out16);
-    VB_LAUNCH_CHECK();
+    VB_CUDA(launch_kernel(attn_decode_combine_kernel, dim3(n_head, B), dim3(HD), 0, s, pdl, (const float *)part_o,
+                          (const float *)part_ml, n_head, ns, out, (bf16 *)out16));
+    count_launch();
   }
   return VB_OK;
 }

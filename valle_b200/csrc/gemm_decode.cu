@@ -6,9 +6,13 @@
 // read exactly once per step at full TMA throughput and 148 SMs are filled by split-K:
 //   grid = (N_out/128 tiles, S splits); CTA (t, s) streams W[t*128 .. +128, k-range(s)] through a
 //   TMA/mbarrier ring into tcgen05.mma (M=128, N=64, K=16), accumulates in 64 TMEM columns, and
-//   writes its fp32 partial tile to a workspace.  The LAST CTA to finish a tile (atomic ticket) sums
-//   the S partials in fixed order 0..S-1 (deterministic) and applies the fused epilogue:
-//   QKV scatter (q rows + KV-cache append), +bias +residual, +bias ReLU -> bf16, or plain logits.
+//   either applies the fused epilogue itself (S == 1: +bias, ReLU -> bf16, residual, QKV scatter) or
+//   writes its fp32 partial tile to partials[split][b][n]; the CONSUMER kernel (residual + LayerNorm,
+//   the KV-cache attention prologue, the sampler) sums the S partials in fixed order 0..S-1, which
+//   keeps the result deterministic and costs no extra launch.
+//   Programmatic dependent launch: barrier/TMEM setup and the first kStages WEIGHT tiles (which do
+//   not depend on the previous kernel) are issued before griddepcontrol.wait, so weight streaming
+//   overlaps the tail of the previous kernel in the CUDA graph.
 //
 // Replaces F.linear at valle/modules/activation.py:408 (in/out-proj), valle/modules/transformer.py:332-334
 // (FFN) and valle/models/valle.py:1039 (ar_predict_layer) for the batched decode step.
@@ -70,13 +74,12 @@ __device__ __forceinline__ void apply_epi(const Epi &e, int n, int b, float v) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                   int num_kb, float *__restrict__ partials, int *__restrict__ tickets, Epi epi) {
+                   int num_kb, float *__restrict__ partials, int ldp, Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kStages * kStageBytes);
   uint64_t *full_bar = bars, *empty_bar = bars + kStages, *tmem_full = bars + 2 * kStages;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
-  int *s_last = reinterpret_cast<int *>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, split = blockIdx.y, splits = gridDim.y;
@@ -85,6 +88,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int kb0 = split * base + min(split, rem);
   const int nkb = base + (split < rem ? 1 : 0);
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_x);
@@ -109,9 +113,18 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
+      // weights do not depend on the previous kernel: fill the ring with W tiles first ...
+      const int pre = min(nkb, kStages);
+      for (int i = 0; i < pre; ++i) {
+        mbar_expect_tx(&full_bar[i], kStageBytes);
+        tma_load_2d(&tmap_w, &full_bar[i], tiles + i * kStageBytes, (kb0 + i) * BK, tile * TM);
+      }
+      pdl_wait();  // ... the activations do
+      for (int i = 0; i < pre; ++i)
+        tma_load_2d(&tmap_x, &full_bar[i], tiles + i * kStageBytes + kWBytes, (kb0 + i) * BK, 0);
       int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < nkb; ++i) {
+      uint32_t phase = 1;  // the ring has wrapped once
+      for (int i = pre; i < nkb; ++i) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t *w_dst = tiles + stage * kStageBytes;
         mbar_expect_tx(&full_bar[stage], kStageBytes);
@@ -152,6 +165,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     const int nl = q * 32 + lane;  // feature within the tile
     const int n = tile * TM + nl;
     float v[TN];
+    pdl_wait();
     if (nkb > 0) {
       mbar_wait(tmem_full, 0);
       tcgen05_fence_after();
@@ -175,28 +189,10 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       if (n < epi.N)
         for (int b = 0; b < epi.B; ++b) apply_epi(epi, n, b, sv[b * TM + nl]);
     } else {
-      float *mine = partials + ((int64_t)(tile * splits + split) * TN) * TM;
+      // partials[split][b][n]: for a fixed row b consecutive lanes write consecutive features
+      float *mine = partials + (int64_t)split * TN * ldp + n;
 #pragma unroll
-      for (int b = 0; b < TN; ++b) __stcg(mine + b * TM + nl, v[b]);
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
-      if (warp == 4 && lane == 0) {
-        const int old = atomicAdd(&tickets[tile], 1);
-        *s_last = (old == splits - 1);
-        if (old == splits - 1) tickets[tile] = 0;  // re-arm for the next launch
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*s_last) {
-        __threadfence();
-        if (n < epi.N) {
-          const float *p0 = partials + ((int64_t)(tile * splits) * TN) * TM + nl;
-          for (int b = 0; b < epi.B; ++b) {
-            float acc = 0.f;
-            for (int s = 0; s < splits; ++s) acc += __ldcg(p0 + ((int64_t)s * TN + b) * TM);
-            apply_epi(epi, n, b, acc);
-          }
-        }
-      }
+      for (int b = 0; b < TN; ++b) mine[(int64_t)b * ldp] = v[b];
     }
   }
   __syncwarp();
@@ -211,8 +207,8 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 }  // namespace dg
 
 size_t gemm_decode_workspace() {
-  // tickets (4 KB) + fp32 partial tiles for every CTA of one launch (tiles * splits <= #SMs, or splits == 1)
-  return 4096 + (size_t)(sm_count() + 64) * dg::TN * dg::TM * sizeof(float);
+  // fp32 partials [splits][64][ldp]: tiles * splits <= #SMs (or splits == 1), ldp = tiles * 128
+  return (size_t)(sm_count() + 32) * dg::TN * dg::TM * sizeof(float);
 }
 
 static int pick_splits(int tiles, int num_kb) {
@@ -221,25 +217,28 @@ static int pick_splits(int tiles, int num_kb) {
   return max(1, min(s, 32));
 }
 
-// workspace layout: [tickets: 1024 ints][partials]
-int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, int N, int K, const float *bias,
-                       int mode, float *out_f32, bf16 *out_bf16, int64_t ld_out, const QkvScatter *qkv,
-                       void *workspace, size_t workspace_bytes, cudaStream_t s) {
+int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, int N, int K, int force_splits,
+                       const float *bias, int mode, float *out_f32, bf16 *out_bf16, int64_t ld_out,
+                       const QkvScatter *qkv, float *partials, size_t partial_bytes, int *out_splits, int *out_ldp,
+                       bool pdl, cudaStream_t s) {
   VB_CHECK_ARG(B >= 1 && B <= dg::TN, "gemm_decode: B=%d not in [1,64]", B);
   VB_CHECK_ARG(K % tc::BK == 0 && ld_act % 8 == 0, "gemm_decode: K %% 64 != 0 or unaligned activations");
   const int tiles = (N + dg::TM - 1) / dg::TM;
   const int num_kb = K / tc::BK;
-  const int splits = pick_splits(tiles, num_kb);
-  const size_t need = 4096 + (size_t)tiles * splits * dg::TN * dg::TM * sizeof(float);
-  VB_CHECK_ARG(workspace_bytes >= need && tiles <= 1024, "gemm_decode: workspace too small (%zu < %zu)",
-               workspace_bytes, need);
+  const int splits = force_splits > 0 ? force_splits : pick_splits(tiles, num_kb);
+  const int ldp = tiles * dg::TM;
+  if (splits > 1)
+    VB_CHECK_ARG(partials && partial_bytes >= (size_t)splits * dg::TN * ldp * sizeof(float),
+                 "gemm_decode: partial buffer too small");
+  if (out_splits) *out_splits = splits;
+  if (out_ldp) *out_ldp = ldp;
   CUtensorMap tw, tx;
   VB_TRY(tc::make_tmap(&tw, W, N, K, K, dg::TM));
   VB_TRY(tc::make_tmap(&tx, act, B, K, ld_act, dg::TN));
   dg::Epi e{};
   e.mode = mode; e.N = N; e.B = B; e.bias = bias;
   e.out_f32 = out_f32; e.out_bf16 = out_bf16; e.ld_out = ld_out;
-  if (mode == DG_QKV) {
+  if (mode == DG_QKV && splits == 1) {
     VB_CHECK_ARG(qkv != nullptr, "gemm_decode: qkv scatter parameters missing");
     e.d = qkv->d; e.head_dim = qkv->head_dim; e.cache_cap = qkv->cache_cap;
     e.kcache = (bf16 *)qkv->kcache; e.vcache = (bf16 *)qkv->vcache;
@@ -253,10 +252,9 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
                                  dg::kSmemBytes));
     attr_set = true;
   }
-  int *tickets = (int *)workspace;
-  float *partials = (float *)((char *)workspace + 4096);
-  dg::gemm_decode_kernel<<<dim3(tiles, splits), dg::kThreads, dg::kSmemBytes, s>>>(tw, tx, num_kb, partials, tickets, e);
-  VB_LAUNCH_CHECK();
+  VB_CUDA(launch_kernel(dg::gemm_decode_kernel, dim3(tiles, splits), dim3(dg::kThreads), dg::kSmemBytes, s, pdl, tw,
+                        tx, num_kb, partials, ldp, e));
+  count_launch();
   return VB_OK;
 }
 

@@ -32,20 +32,35 @@ __device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
 }
 
 __global__ void __launch_bounds__(256)
-ar_sample_kernel(const float *__restrict__ logits, int64_t ld_logits, int n_vocab, int eos_id,
+ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__restrict__ partials, int splits,
+                 int ldp, int n_vocab, int eos_id,
                  const float *__restrict__ audio_emb, const float *__restrict__ alpha,
                  const float *__restrict__ pe, int pe_rows, const int32_t *__restrict__ text_len,
                  const int32_t *__restrict__ prompt_len, const int32_t *__restrict__ max_new,
                  int32_t *__restrict__ n_gen, int32_t *__restrict__ finished,
                  int32_t *__restrict__ tokens, int tok_stride, float *__restrict__ x_cur, int d,
-                 const int64_t *__restrict__ forced) {
+                 const int64_t *__restrict__ forced, int reduce_only) {
   __shared__ ArgMax wbest[8];
   __shared__ int s_tok, s_pos;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (finished[b] != 0) return;  // uniform per CTA
-  const float *row = logits + (int64_t)b * ld_logits;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (finished[b] != 0 && !reduce_only) return;  // uniform per CTA
+  float *row = logits + (int64_t)b * ld_logits;
   ArgMax best{-CUDART_INF_F, 0x7fffffff};
-  for (int i = tid; i < n_vocab; i += 256) best = better(best, ArgMax{row[i], i});
+  for (int i = tid; i < n_vocab; i += 256) {
+    float v;
+    if (partials) {  // split-K partials of the head projection, summed in fixed order
+      const float *p = partials + (int64_t)b * ldp + i;
+      v = p[0];
+      for (int s = 1; s < splits; ++s) v += p[(int64_t)s * 64 * ldp];
+      row[i] = v;
+    } else {
+      v = row[i];
+    }
+    best = better(best, ArgMax{v, i});
+  }
+  if (reduce_only) return;
   best = warp_argmax(best);
   if (lane == 0) wbest[warp] = best;
   __syncthreads();
@@ -85,13 +100,14 @@ ar_sample_kernel(const float *__restrict__ logits, int64_t ld_logits, int n_voca
   }
 }
 
-int launch_ar_sample(const float *logits, int64_t ld_logits, const vb_ar_head *head, vb_ar_state *st,
-                     int d, const int64_t *forced, cudaStream_t s) {
-  ar_sample_kernel<<<st->B, 256, 0, s>>>(logits, ld_logits, head->n_vocab, head->eos_id, head->audio_emb,
-                                         head->alpha, head->pe, head->pe_rows, st->text_len,
-                                         st->prompt_len, st->max_new, st->n_gen, st->finished, st->tokens,
-                                         st->tok_stride, st->x_cur, d, forced);
-  VB_LAUNCH_CHECK();
+int launch_ar_sample(float *logits, int64_t ld_logits, const float *partials, int splits, int ldp,
+                     const vb_ar_head *head, vb_ar_state *st, int d, const int64_t *forced, int reduce_only, bool pdl,
+                     cudaStream_t s) {
+  VB_CUDA(launch_kernel(ar_sample_kernel, dim3(st->B), dim3(256), 0, s, pdl, logits, ld_logits, partials, splits, ldp,
+                        head->n_vocab, head->eos_id, head->audio_emb, head->alpha, head->pe, head->pe_rows,
+                        (const int32_t *)st->text_len, (const int32_t *)st->prompt_len, (const int32_t *)st->max_new,
+                        st->n_gen, st->finished, st->tokens, st->tok_stride, st->x_cur, d, forced, reduce_only));
+  count_launch();
   return VB_OK;
 }
 
