@@ -261,8 +261,10 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
                                 nullptr, d, nullptr, P, w.gemm_ws_bytes, &s2, &ldp2, pdl, s));
       VB_TRY(launch_ln_reduce(x, d, B, d, s2 > 1 ? P : nullptr, s2, ldp2, L.out_proj_b, L.norm2_w, L.norm2_b, 1e-5f,
                               w.xn16, pdl, s));
-      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.lin1_w, dff, d, 1, L.lin1_b, DG_RELU_BF16, nullptr,
-                                w.hb16, dff, nullptr, P, w.gemm_ws_bytes, nullptr, nullptr, pdl, s));
+      int sf = 1, ldpf = 0;
+      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.lin1_w, dff, d, 0, L.lin1_b, DG_RELU_BF16, nullptr,
+                                w.hb16, dff, nullptr, P, w.gemm_ws_bytes, &sf, &ldpf, pdl, s));
+      if (sf > 1) VB_TRY(launch_relu_reduce(P, sf, ldpf, L.lin1_b, B, dff, w.hb16, dff, pdl, s));
       int s3 = 1, ldp3 = 0;
       VB_TRY(launch_gemm_decode(w.hb16, B, dff, (const bf16 *)L.lin2_w, d, dff, 0, L.lin2_b, DG_RESIDUAL, x, nullptr,
                                 d, nullptr, P, w.gemm_ws_bytes, &s3, &ldp3, pdl, s));

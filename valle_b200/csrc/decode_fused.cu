@@ -8,29 +8,32 @@
 
 namespace vb {
 
-template <int kVecs>
-__global__ void __launch_bounds__(128)
+// one CTA (256 threads) per row: every thread owns 4 consecutive features per 1024-wide slab, sums the
+// S partials with independent loads in flight, then the block reduces the LayerNorm moments.
+template <int kSlabs>
+__global__ void __launch_bounds__(256)
 ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *__restrict__ partials, int splits,
                  int ldp, const float *__restrict__ bias, const float *__restrict__ gamma,
                  const float *__restrict__ beta, float eps, bf16 *__restrict__ out16) {
+  __shared__ float red[2][8];
   pdl_launch_dependents();
-  const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();
-  if (b >= B) return;
   float *xr = x + (int64_t)b * ldx;
-  float4 v[kVecs];
+  float4 v[kSlabs];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kVecs; ++i) {
-    const int c = (i * 32 + lane) * 4;
+  for (int i = 0; i < kSlabs; ++i) {
+    const int c = (i * 256 + tid) * 4;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < d) {
       v[i] = *reinterpret_cast<const float4 *>(xr + c);
       if (partials) {
         const float *p = partials + (int64_t)b * ldp + c;
-        float4 a = *reinterpret_cast<const float4 *>(p);
+        float4 a = __ldcg(reinterpret_cast<const float4 *>(p));
+#pragma unroll 6
         for (int sidx = 1; sidx < splits; ++sidx) {
-          const float4 t = *reinterpret_cast<const float4 *>(p + (int64_t)sidx * 64 * ldp);
+          const float4 t = __ldcg(reinterpret_cast<const float4 *>(p + (int64_t)sidx * 64 * ldp));
           a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
         }
         if (bias) {
@@ -41,25 +44,35 @@ ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *
         *reinterpret_cast<float4 *>(xr + c) = v[i];
       }
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    } else {
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  const float mean = warp_sum(s) / (float)d;
+  s = warp_sum(s);
+  if (lane == 0) red[0][warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[0][w];
+  const float mean = tot / (float)d;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < kVecs; ++i) {
-    const int c = (i * 32 + lane) * 4;
+  for (int i = 0; i < kSlabs; ++i) {
+    const int c = (i * 256 + tid) * 4;
     if (c < d) {
       const float a = v[i].x - mean, bq = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
       q += (a * a + bq * bq) + (e * e + f * f);
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+  q = warp_sum(q);
+  if (lane == 0) red[1][warp] = q;
+  __syncthreads();
+  float qt = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) qt += red[1][w];
+  const float rstd = rsqrtf(qt / (float)d + eps);
   bf16 *orow = out16 + (int64_t)b * d;
 #pragma unroll
-  for (int i = 0; i < kVecs; ++i) {
-    const int c = (i * 32 + lane) * 4;
+  for (int i = 0; i < kSlabs; ++i) {
+    const int c = (i * 256 + tid) * 4;
     if (c < d) {
       const float4 g = *reinterpret_cast<const float4 *>(gamma + c);
       const float4 be = *reinterpret_cast<const float4 *>(beta + c);
@@ -73,20 +86,55 @@ ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *
   }
 }
 
+// out16[b, n] = bf16(relu(bias[n] + sum_s partials[s][b][n]))  -- FFN hidden activation
+// (valle/modules/transformer.py:332-334: linear1 -> ReLU), input rows of the linear2 projection.
+__global__ void __launch_bounds__(256)
+relu_reduce_kernel(const float *__restrict__ partials, int splits, int ldp, const float *__restrict__ bias, int N,
+                   bf16 *__restrict__ out16, int64_t ldo) {
+  pdl_launch_dependents();
+  const int b = blockIdx.y;
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  pdl_wait();
+  if (c >= N) return;
+  const float *p = partials + (int64_t)b * ldp + c;
+  float4 a = __ldcg(reinterpret_cast<const float4 *>(p));
+#pragma unroll 4
+  for (int s = 1; s < splits; ++s) {
+    const float4 t = __ldcg(reinterpret_cast<const float4 *>(p + (int64_t)s * 64 * ldp));
+    a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+  }
+  const float4 bb = *reinterpret_cast<const float4 *>(bias + c);
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(a.x + bb.x, 0.f), fmaxf(a.y + bb.y, 0.f));
+  __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(a.z + bb.z, 0.f), fmaxf(a.w + bb.w, 0.f));
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t *>(&p0);
+  pk.y = *reinterpret_cast<uint32_t *>(&p1);
+  *reinterpret_cast<uint2 *>(out16 + (int64_t)b * ldo + c) = pk;
+}
+
+int launch_relu_reduce(const float *partials, int splits, int ldp, const float *bias, int B, int N, bf16 *out16,
+                       int64_t ldo, bool pdl, cudaStream_t s) {
+  VB_CHECK_ARG(N % 4 == 0 && ldo % 4 == 0, "relu_reduce: N %% 4 != 0");
+  VB_CUDA(launch_kernel(relu_reduce_kernel, dim3((N / 4 + 255) / 256, B), dim3(256), 0, s, pdl, partials, splits, ldp,
+                        bias, N, out16, ldo));
+  count_launch();
+  return VB_OK;
+}
+
 int launch_ln_reduce(float *x, int64_t ldx, int B, int d, const float *partials, int splits, int ldp,
                      const float *bias, const float *gamma, const float *beta, float eps, bf16 *out16, bool pdl,
                      cudaStream_t s) {
-  VB_CHECK_ARG(d % 4 == 0 && ldx % 4 == 0 && d <= 2048, "ln_reduce: bad d=%d", d);
-  const dim3 grid((B + 3) / 4), block(128);
-  const int vecs = (d + 127) / 128;
-  if (vecs <= 2)
+  VB_CHECK_ARG(d % 4 == 0 && ldx % 4 == 0 && d <= 4096, "ln_reduce: bad d=%d", d);
+  const dim3 grid(B), block(256);
+  const int slabs = (d + 1023) / 1024;
+  if (slabs <= 1)
+    VB_CUDA(launch_kernel(ln_reduce_kernel<1>, grid, block, 0, s, pdl, x, ldx, B, d, partials, splits, ldp, bias,
+                          gamma, beta, eps, out16));
+  else if (slabs <= 2)
     VB_CUDA(launch_kernel(ln_reduce_kernel<2>, grid, block, 0, s, pdl, x, ldx, B, d, partials, splits, ldp, bias,
                           gamma, beta, eps, out16));
-  else if (vecs <= 8)
-    VB_CUDA(launch_kernel(ln_reduce_kernel<8>, grid, block, 0, s, pdl, x, ldx, B, d, partials, splits, ldp, bias,
-                          gamma, beta, eps, out16));
   else
-    VB_CUDA(launch_kernel(ln_reduce_kernel<16>, grid, block, 0, s, pdl, x, ldx, B, d, partials, splits, ldp, bias,
+    VB_CUDA(launch_kernel(ln_reduce_kernel<4>, grid, block, 0, s, pdl, x, ldx, B, d, partials, splits, ldp, bias,
                           gamma, beta, eps, out16));
   count_launch();
   return VB_OK;

@@ -54,6 +54,8 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
                        const int32_t *n_gen, float *out, void *out16, void *workspace, bool pdl, cudaStream_t s);
 
 // decode_fused.cu
+int launch_relu_reduce(const float *partials, int splits, int ldp, const float *bias, int B, int N, bf16 *out16,
+                       int64_t ldo, bool pdl, cudaStream_t s);
 int launch_ln_reduce(float *x, int64_t ldx, int B, int d, const float *partials, int splits, int ldp,
                      const float *bias, const float *gamma, const float *beta, float eps, bf16 *out16, bool pdl,
                      cudaStream_t s);

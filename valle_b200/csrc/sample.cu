@@ -52,8 +52,9 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
     float v;
     if (partials) {  // split-K partials of the head projection, summed in fixed order
       const float *p = partials + (int64_t)b * ldp + i;
-      v = p[0];
-      for (int s = 1; s < splits; ++s) v += p[(int64_t)s * 64 * ldp];
+      v = __ldcg(p);
+#pragma unroll 8
+      for (int s = 1; s < splits; ++s) v += __ldcg(p + (int64_t)s * 64 * ldp);
       row[i] = v;
     } else {
       v = row[i];
