@@ -49,9 +49,10 @@ def gather_codes(codes: Sequence[torch.Tensor], n_q: int, device, b_max: int = N
     if block.shape[0] < bm:
         block = torch.cat([block, torch.zeros((bm - block.shape[0], tm, n_q), dtype=block.dtype, device=device)])
         lens = torch.cat([lens, torch.zeros(bm - lens.shape[0], dtype=lens.dtype, device=device)])
+    assert n_q % 2 == 0, "codes travel as int16 pairs viewed as int32 (gloo has no int16 collectives)"
     all_blocks = torch.empty((world * bm, tm, n_q), dtype=torch.int16, device=device)
     all_lens = torch.empty(world * bm, dtype=torch.int32, device=device)
-    dist.all_gather_into_tensor(all_blocks, block.contiguous())
+    dist.all_gather_into_tensor(all_blocks.view(torch.int32), block.contiguous().view(torch.int32))
     dist.all_gather_into_tensor(all_lens, lens.contiguous())
     all_lens_h = all_lens.cpu()
     out = []
