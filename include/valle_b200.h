@@ -34,8 +34,14 @@ enum vb_epilogue { VB_EPI_NONE = 0, VB_EPI_RELU = 1, VB_EPI_RESIDUAL = 2 };
 /* attention visibility rule */
 enum vb_mask_mode {
   VB_MASK_FULL = 0,    /* NAR: every row of a sequence sees the whole sequence (valle.py:1125-1127) */
-  VB_MASK_VALLE_AR = 1 /* AR: text rows see all text, audio rows see text + causal audio
-                          (valle.py:1010-1033): kv_len(i) = max(S, i + 1) */
+  VB_MASK_VALLE_AR = 1, /* AR inference: text rows see all text, audio rows see text + causal audio
+                           (valle.py:1010-1033): kv_len(i) = max(S, i + 1) */
+  /* padded training batches (valle.py:804-861,908-925): every sequence is [text padded to
+     seg1_start | audio padded]; valid keys are text [0, text_lens[b]) and audio
+     [seg1_start, seg1_start + seg1_lens[b]). */
+  VB_MASK_PADDED_AR = 2, /* + text rows see text only, audio rows causal (the merged
+                            attn_mask | key_padding_mask of valle.py:835-861) */
+  VB_MASK_PADDED = 3     /* key padding only (NAR training, valle.py:921-925) */
 };
 
 typedef void *vb_stream_t; /* cudaStream_t */
@@ -97,9 +103,9 @@ int vb_linear(const void *A, int a_dtype, int64_t lda, const void *W, int w_dtyp
  *   VB_MASK_VALLE_AR).  out: [M, d].  If kcache != NULL the K and V rows are also written to
  *   the caches ([B, H, cache_cap, hd], dtype = dtype) at their sequence position. */
 int vb_attention(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
-                 const int32_t *cu_seqlens, const int32_t *text_lens, int max_seqlen, int mask_mode,
-                 void *out, void *kcache, void *vcache, int64_t cache_seq_stride, int cache_cap,
-                 vb_stream_t stream);
+                 const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start,
+                 int max_seqlen, int mask_mode, void *out, void *kcache, void *vcache,
+                 int64_t cache_seq_stride, int cache_cap, vb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Decoder stack handle (transformer.py:337-406 TransformerEncoder of pre-LN
@@ -140,7 +146,8 @@ size_t vb_decoder_forward_workspace(const vb_decoder_desc *desc, int64_t M);
  *   current stage: row 2l = layer l norm1, 2l+1 = layer l norm2, last = final norm.
  *   kcache/vcache: NULL or [n_layer, B, H, cache_cap, hd] caches filled for later decoding. */
 int vb_decoder_forward(vb_decoder_t dec, float *x, int64_t M, int B, const int32_t *cu_seqlens,
-                       const int32_t *text_lens, int max_seqlen, int mask_mode, const float *ada_wb,
+                       const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
+                       int mask_mode, const float *ada_wb,
                        void *kcache, void *vcache, int64_t cache_layer_stride,
                        int64_t cache_seq_stride, int cache_cap, void *workspace,
                        size_t workspace_bytes, vb_stream_t stream);
@@ -205,6 +212,12 @@ int vb_nar_argmax_accumulate(const float *logits, int64_t n_rows, int n_vocab, i
                              int64_t *codes, int64_t code_row_stride, const float *next_emb,
                              float *y_emb, int64_t y_row_stride, const int32_t *y_rows, int d,
                              vb_stream_t stream);
+
+/* a2  F.cross_entropy of VALLE.forward (valle.py:877,936-941), per row:
+ *   loss[r] = logsumexp(logits[r,:]) - logits[r, targets[r]], 0 where targets[r] == ignore_index
+ *   (pass ignore_index = -1 for none).  The caller sums (reduction="sum"). */
+int vb_cross_entropy(const float *logits, int64_t ld_logits, const int64_t *targets, int64_t n_rows,
+                     int n_vocab, int64_t ignore_index, float *loss, vb_stream_t stream);
 
 /* gather rows: dst[r,:] = src[rows[r],:]  (fp32), used for "last position" / target slices */
 int vb_gather_rows(const float *src, int64_t src_row_stride, const int32_t *rows, int64_t n_rows,

@@ -86,7 +86,8 @@ VB_API size_t vb_decoder_forward_workspace(const vb_decoder_desc *desc, int64_t 
 }
 
 VB_API int vb_decoder_forward(vb_decoder_t dec, float *x, int64_t M, int B, const int32_t *cu_seqlens,
-                                  const int32_t *text_lens, int max_seqlen, int mask_mode,
+                                  const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start,
+                                  int max_seqlen, int mask_mode,
                                   const float *ada_wb, void *kcache, void *vcache,
                                   int64_t cache_layer_stride, int64_t cache_seq_stride, int cache_cap,
                                   void *workspace, size_t workspace_bytes, vb_stream_t stream) {
@@ -114,7 +115,7 @@ VB_API int vb_decoder_forward(vb_decoder_t dec, float *x, int64_t M, int B, cons
                      nullptr, 0, stream));
     void *kc = kcache ? (char *)kcache + (size_t)l * cache_layer_stride * ts : nullptr;
     void *vc = vcache ? (char *)vcache + (size_t)l * cache_layer_stride * ts : nullptr;
-    VB_TRY(launch_attention_varlen(qkv, dt, M, B, D.n_head, d / D.n_head, cu_seqlens, text_lens, max_seqlen,
+    VB_TRY(launch_attention_varlen(qkv, dt, M, B, D.n_head, d / D.n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, max_seqlen,
                                    mask_mode, att, kc, vc, cache_seq_stride, cache_cap, s));
     VB_TRY(vb_linear(att, dt, d, P.out_proj_w, dt, P.out_proj_b, x, VB_F32, d, M, d, d, VB_EPI_RESIDUAL,
                      nullptr, 0, stream));

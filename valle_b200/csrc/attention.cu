@@ -23,7 +23,8 @@ static constexpr int HD = 64;
 template <typename T>
 __global__ void __launch_bounds__(256)
 attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__restrict__ cu_seqlens,
-                        const int32_t *__restrict__ text_lens, int mask_mode, T *__restrict__ out,
+                        const int32_t *__restrict__ text_lens, const int32_t *__restrict__ seg1_lens,
+                        int seg1_start, int mask_mode, T *__restrict__ out,
                         T *__restrict__ kcache, T *__restrict__ vcache, int64_t cache_seq_stride,
                         int cache_cap) {
   constexpr int LDT = 68;  // padded leading dim (floats), keeps float4 alignment
@@ -37,7 +38,8 @@ attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__
   const int r0 = cu_seqlens[b], L = cu_seqlens[b + 1] - r0;
   const int q0 = blockIdx.x * 64;
   if (q0 >= L) return;
-  const int S = (mask_mode == VB_MASK_VALLE_AR) ? text_lens[b] : 0;
+  const int S = (mask_mode != VB_MASK_FULL) ? text_lens[b] : 0;
+  const int c1 = (mask_mode >= VB_MASK_PADDED_AR) ? seg1_lens[b] : 0;
   const int d = n_head * HD;
   const int64_t ld = 3 * (int64_t)d;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -50,12 +52,9 @@ attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__
 #pragma unroll
     for (int i = 0; i < 16; ++i) Qt[(le0 + i) * LDT + lrow] = (qr < L) ? to_f32(src[i]) : 0.f;
   }
-  int lim[4];  // kv_len per owned row
+  RowMask lim[4];  // visibility rule per owned row
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int qr = q0 + ty * 4 + i;
-    lim[i] = qr >= L ? 0 : (mask_mode == VB_MASK_VALLE_AR ? max(S, qr + 1) : L);
-  }
+  for (int i = 0; i < 4; ++i) lim[i] = make_row_mask(mask_mode, q0 + ty * 4 + i, L, S, seg1_start, c1);
   const int q_hi = min(q0 + 64, L);
   const int kv_max = (mask_mode == VB_MASK_VALLE_AR) ? max(S, q_hi) : L;
 
@@ -120,7 +119,7 @@ attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = j0 + tx * 4 + j;
-        s[i][j] = (c < lim[i]) ? s[i][j] * 0.125f : -CUDART_INF_F;
+        s[i][j] = lim[i].ok(c) ? s[i][j] * 0.125f : -CUDART_INF_F;
         mx = fmaxf(mx, s[i][j]);
       }
 #pragma unroll
@@ -172,26 +171,27 @@ attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__
 }
 
 int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
-                            const int32_t *cu_seqlens, const int32_t *text_lens, int max_seqlen,
-                            int mask_mode, void *out, void *kcache, void *vcache,
+                            const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,
+                            int seg1_start, int max_seqlen, int mask_mode, void *out, void *kcache, void *vcache,
                             int64_t cache_seq_stride, int cache_cap, cudaStream_t s) {
   VB_CHECK_ARG(head_dim == HD, "attention: head_dim=%d, only 64 is built", head_dim);
-  VB_CHECK_ARG(mask_mode == VB_MASK_FULL || text_lens != nullptr, "attention: AR mask needs text_lens");
+  VB_CHECK_ARG(mask_mode == VB_MASK_FULL || text_lens != nullptr, "attention: this mask mode needs text_lens");
+  VB_CHECK_ARG(mask_mode < VB_MASK_PADDED_AR || seg1_lens != nullptr, "attention: padded mask modes need seg1_lens");
   if (M == 0 || B == 0) return VB_OK;
   const size_t smem = 4 * 64 * 68 * sizeof(float);
   dim3 grid((max_seqlen + 63) / 64, n_head, B);
   if (dtype == VB_F32) {
     auto k = attn_varlen_simt_kernel<float>;
     VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, s>>>((const float *)qkv, n_head, cu_seqlens, text_lens, mask_mode, (float *)out,
+    k<<<grid, 256, smem, s>>>((const float *)qkv, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, (float *)out,
                               (float *)kcache, (float *)vcache, cache_seq_stride, cache_cap);
   } else if (dtype == VB_BF16 && getenv("VB_ATTN_SIMT") == nullptr) {
-    return launch_attention_mma((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, max_seqlen, mask_mode,
+    return launch_attention_mma((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, max_seqlen, mask_mode,
                                 (bf16 *)out, (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, s);
   } else if (dtype == VB_BF16) {
     auto k = attn_varlen_simt_kernel<bf16>;
     VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, 256, smem, s>>>((const bf16 *)qkv, n_head, cu_seqlens, text_lens, mask_mode, (bf16 *)out,
+    k<<<grid, 256, smem, s>>>((const bf16 *)qkv, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, (bf16 *)out,
                               (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap);
   } else {
     set_error("attention: bad dtype %d", dtype);
@@ -440,10 +440,10 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
 }  // namespace vb
 
 VB_API int vb_attention(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
-                            const int32_t *cu_seqlens, const int32_t *text_lens, int max_seqlen,
-                            int mask_mode, void *out, void *kcache, void *vcache,
-                            int64_t cache_seq_stride, int cache_cap, vb_stream_t stream) {
-  return vb::launch_attention_varlen(qkv, dtype, M, B, n_head, head_dim, cu_seqlens, text_lens, max_seqlen,
-                                     mask_mode, out, kcache, vcache, cache_seq_stride, cache_cap,
+                        const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start,
+                        int max_seqlen, int mask_mode, void *out, void *kcache, void *vcache,
+                        int64_t cache_seq_stride, int cache_cap, vb_stream_t stream) {
+  return vb::launch_attention_varlen(qkv, dtype, M, B, n_head, head_dim, cu_seqlens, text_lens, seg1_lens, seg1_start,
+                                     max_seqlen, mask_mode, out, kcache, vcache, cache_seq_stride, cache_cap,
                                      (cudaStream_t)stream);
 }

@@ -68,7 +68,8 @@ __device__ __forceinline__ void load_tile(uint8_t *smem_tile, const bf16 *base, 
 
 __global__ void __launch_bounds__(kThreads)
 attn_varlen_mma_kernel(const bf16 *__restrict__ qkv, int n_head, const int32_t *__restrict__ cu_seqlens,
-                       const int32_t *__restrict__ text_lens, int mask_mode, bf16 *__restrict__ out,
+                       const int32_t *__restrict__ text_lens, const int32_t *__restrict__ seg1_lens,
+                       int seg1_start, int mask_mode, bf16 *__restrict__ out,
                        bf16 *__restrict__ kcache, bf16 *__restrict__ vcache, int64_t cache_seq_stride,
                        int cache_cap) {
   __shared__ __align__(128) uint8_t sQ[BQ * 128];
@@ -79,7 +80,8 @@ attn_varlen_mma_kernel(const bf16 *__restrict__ qkv, int n_head, const int32_t *
   const int r0 = cu_seqlens[b], L = cu_seqlens[b + 1] - r0;
   const int q0 = blockIdx.x * BQ;
   if (q0 >= L) return;
-  const int S = (mask_mode == VB_MASK_VALLE_AR) ? text_lens[b] : 0;
+  const int S = (mask_mode != VB_MASK_FULL) ? text_lens[b] : 0;
+  const int c1 = (mask_mode >= VB_MASK_PADDED_AR) ? seg1_lens[b] : 0;
   const int d = n_head * HD;
   const int64_t ld = 3 * (int64_t)d;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -99,14 +101,8 @@ attn_varlen_mma_kernel(const bf16 *__restrict__ qkv, int n_head, const int32_t *
 
   // per-thread rows: g and g + 8 of this warp's 16-row slab
   const int row_a = q0 + warp * 16 + g, row_b = row_a + 8;
-  int lim_a, lim_b;
-  if (mask_mode == VB_MASK_VALLE_AR) {
-    lim_a = row_a < L ? max(S, row_a + 1) : 0;
-    lim_b = row_b < L ? max(S, row_b + 1) : 0;
-  } else {
-    lim_a = row_a < L ? L : 0;
-    lim_b = row_b < L ? L : 0;
-  }
+  const RowMask lim_a = make_row_mask(mask_mode, row_a, L, S, seg1_start, c1);
+  const RowMask lim_b = make_row_mask(mask_mode, row_b, L, S, seg1_start, c1);
 
   uint32_t qf[4][4];  // A fragments of Q: 4 k-steps over head_dim
   float o[8][4];
@@ -172,10 +168,10 @@ attn_varlen_mma_kernel(const bf16 *__restrict__ qkv, int n_head, const int32_t *
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int c = j0 + nt * 8 + t4 * 2;
-      s[nt][0] = (c < lim_a) ? s[nt][0] * sc : -CUDART_INF_F;
-      s[nt][1] = (c + 1 < lim_a) ? s[nt][1] * sc : -CUDART_INF_F;
-      s[nt][2] = (c < lim_b) ? s[nt][2] * sc : -CUDART_INF_F;
-      s[nt][3] = (c + 1 < lim_b) ? s[nt][3] * sc : -CUDART_INF_F;
+      s[nt][0] = lim_a.ok(c) ? s[nt][0] * sc : -CUDART_INF_F;
+      s[nt][1] = lim_a.ok(c + 1) ? s[nt][1] * sc : -CUDART_INF_F;
+      s[nt][2] = lim_b.ok(c) ? s[nt][2] * sc : -CUDART_INF_F;
+      s[nt][3] = lim_b.ok(c + 1) ? s[nt][3] * sc : -CUDART_INF_F;
       mx_a = fmaxf(mx_a, fmaxf(s[nt][0], s[nt][1]));
       mx_b = fmaxf(mx_b, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -245,11 +241,12 @@ attn_varlen_mma_kernel(const bf16 *__restrict__ qkv, int n_head, const int32_t *
 }  // namespace fa
 
 int launch_attention_mma(const bf16 *qkv, int64_t M, int B, int n_head, const int32_t *cu_seqlens,
-                         const int32_t *text_lens, int max_seqlen, int mask_mode, bf16 *out, bf16 *kcache,
+                         const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
+                         int mask_mode, bf16 *out, bf16 *kcache,
                          bf16 *vcache, int64_t cache_seq_stride, int cache_cap, cudaStream_t s) {
   if (M == 0 || B == 0) return VB_OK;
   dim3 grid((max_seqlen + fa::BQ - 1) / fa::BQ, n_head, B);
-  fa::attn_varlen_mma_kernel<<<grid, fa::kThreads, 0, s>>>(qkv, n_head, cu_seqlens, text_lens, mask_mode, out,
+  fa::attn_varlen_mma_kernel<<<grid, fa::kThreads, 0, s>>>(qkv, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, out,
                                                           kcache, vcache, cache_seq_stride, cache_cap);
   VB_LAUNCH_CHECK();
   return VB_OK;

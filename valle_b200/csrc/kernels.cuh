@@ -4,6 +4,27 @@
 
 namespace vb {
 
+// Visibility rule of one query row (see vb_mask_mode): key c is seen iff c < lim0 or s1 <= c < hi1.
+struct RowMask {
+  int lim0, s1, hi1;
+  __device__ __forceinline__ bool ok(int c) const { return c < lim0 || (c >= s1 && c < hi1); }
+};
+__device__ __forceinline__ RowMask make_row_mask(int mode, int qr, int L, int S, int seg1_start, int seg1_len) {
+  RowMask m{0, 0, 0};
+  if (qr >= L) return m;
+  if (mode == VB_MASK_FULL) {
+    m.lim0 = L; m.s1 = L; m.hi1 = L;
+  } else if (mode == VB_MASK_VALLE_AR) {
+    m.lim0 = max(S, qr + 1); m.s1 = L; m.hi1 = L;
+  } else if (mode == VB_MASK_PADDED_AR) {
+    m.lim0 = S; m.s1 = seg1_start;
+    m.hi1 = qr >= seg1_start ? seg1_start + min(seg1_len, qr - seg1_start + 1) : seg1_start;
+  } else {  // VB_MASK_PADDED
+    m.lim0 = S; m.s1 = seg1_start; m.hi1 = seg1_start + seg1_len;
+  }
+  return m;
+}
+
 struct LnParams {
   const float *gamma, *beta, *ada_wb;  // ada_wb: NULL or [2d] (weight | bias)
   float eps;
@@ -40,12 +61,13 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
 
 // attention.cu
 int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
-                            const int32_t *cu_seqlens, const int32_t *text_lens, int max_seqlen,
-                            int mask_mode, void *out, void *kcache, void *vcache,
+                            const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,
+                            int seg1_start, int max_seqlen, int mask_mode, void *out, void *kcache, void *vcache,
                             int64_t cache_seq_stride, int cache_cap, cudaStream_t s);
 // attention_mma.cu (bf16 tensor-core flash attention)
 int launch_attention_mma(const bf16 *qkv, int64_t M, int B, int n_head, const int32_t *cu_seqlens,
-                         const int32_t *text_lens, int max_seqlen, int mask_mode, bf16 *out, bf16 *kcache,
+                         const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
+                         int mask_mode, bf16 *out, bf16 *kcache,
                          bf16 *vcache, int64_t cache_seq_stride, int cache_cap, cudaStream_t s);
 size_t attn_decode_workspace(int B, int n_head, int head_dim, int cache_cap);
 int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, int qkv_ldp, const float *qkv_bias,

@@ -156,3 +156,33 @@ VB_API int vb_nar_argmax_accumulate(const float *logits, int64_t n_rows, int n_v
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
+
+// F.cross_entropy per row (valle/models/valle.py:877,936-941): loss[r] = logsumexp(logits[r,:]) -
+// logits[r, target[r]]; rows whose target == ignore_index contribute 0.  One warp per row, fp32.
+namespace vb {
+__global__ void cross_entropy_kernel(const float *__restrict__ logits, int64_t ld, const int64_t *__restrict__ targets,
+                                     int64_t n_rows, int n_vocab, int64_t ignore_index, float *__restrict__ loss) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  const float *row = logits + r * ld;
+  const int64_t tg = targets[r];
+  float mx = -CUDART_INF_F;
+  for (int i = lane; i < n_vocab; i += 32) mx = fmaxf(mx, row[i]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int i = lane; i < n_vocab; i += 32) s += expf(row[i] - mx);
+  s = warp_sum(s);
+  if (lane == 0) loss[r] = (tg == ignore_index || tg < 0 || tg >= n_vocab) ? 0.f : (logf(s) + mx - row[tg]);
+}
+}  // namespace vb
+
+VB_API int vb_cross_entropy(const float *logits, int64_t ld_logits, const int64_t *targets, int64_t n_rows,
+                            int n_vocab, int64_t ignore_index, float *loss, vb_stream_t stream) {
+  if (n_rows == 0) return VB_OK;
+  const int wpb = 4;
+  vb::cross_entropy_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      logits, ld_logits, targets, n_rows, n_vocab, ignore_index, loss);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}

@@ -298,7 +298,8 @@ class NativeDecoder:
 
     def forward(self, x: Tensor, cu_seqlens: Tensor, B: int, max_seqlen: int, mask_mode: int,
                 text_lens: Optional[Tensor], ada: Optional[Tensor], kcache: Optional[Tensor] = None,
-                vcache: Optional[Tensor] = None, cache_cap: int = 0) -> Tensor:
+                vcache: Optional[Tensor] = None, cache_cap: int = 0, seg1_lens: Optional[Tensor] = None,
+                seg1_start: int = 0) -> Tensor:
         """In-place stack forward over packed rows x [M, d] fp32 (no final norm)."""
         M = x.shape[0]
         nbytes = self.lib.vb_decoder_forward_workspace(C.byref(self.desc), M)
@@ -307,7 +308,7 @@ class NativeDecoder:
         if kcache is not None:  # [n_layer, B, H, cap, hd]
             ls, ss = kcache.stride(0), kcache.stride(1)
         L.check(self.lib.vb_decoder_forward(self.handle, x.data_ptr(), M, B, cu_seqlens.data_ptr(),
-                                            L.ptr(text_lens), max_seqlen, mask_mode, L.ptr(ada),
+                                            L.ptr(text_lens), L.ptr(seg1_lens), seg1_start, max_seqlen, mask_mode, L.ptr(ada),
                                             L.ptr(kcache), L.ptr(vcache), ls, ss, cache_cap,
                                             ws.data_ptr(), ws.numel(), L.stream_ptr()), "vb_decoder_forward")
         return x

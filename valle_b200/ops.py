@@ -102,7 +102,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
 def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, n_head: int,
               mask_mode: int = L.VB_MASK_FULL, text_lens: Optional[torch.Tensor] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, seg1_lens: Optional[torch.Tensor] = None,
+              seg1_start: int = 0) -> torch.Tensor:
     """softmax(q k^T / sqrt(hd) + mask) v over packed ragged sequences (activation.py:408-427)."""
     _req_cuda(qkv, cu_seqlens, text_lens)
     M, d3 = qkv.shape
@@ -111,7 +112,8 @@ def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, n_he
         out = torch.empty((M, d), dtype=qkv.dtype, device=qkv.device)
     B = cu_seqlens.numel() - 1
     L.check(L.load().vb_attention(qkv.data_ptr(), _DT[qkv.dtype], M, B, n_head, d // n_head, cu_seqlens.data_ptr(),
-                                  L.ptr(text_lens), max_seqlen, mask_mode, out.data_ptr(), 0, 0, 0, 0, _stream()),
+                                  L.ptr(text_lens), L.ptr(seg1_lens), seg1_start, max_seqlen, mask_mode, out.data_ptr(), 0, 0, 0, 0,
+                                  _stream()),
             "vb_attention")
     return out
 
@@ -138,3 +140,14 @@ def nar_argmax_accumulate(logits: torch.Tensor, codes: torch.Tensor, code_row_st
                                               code_row_stride, L.ptr(next_emb), L.ptr(y_emb),
                                               y_emb.stride(0) if y_emb is not None else 0, L.ptr(y_rows), d, _stream()),
             "vb_nar_argmax_accumulate")
+
+
+def cross_entropy_rows(logits: torch.Tensor, targets: torch.Tensor, ignore_index: int = -1) -> torch.Tensor:
+    """per-row F.cross_entropy (valle.py:877,936-941); ignored rows give 0."""
+    _req_cuda(logits, targets)
+    assert logits.dtype == torch.float32 and targets.dtype == torch.int64 and logits.dim() == 2
+    n, V = logits.shape
+    out = torch.empty(n, dtype=torch.float32, device=logits.device)
+    L.check(L.load().vb_cross_entropy(logits.data_ptr(), logits.stride(0), targets.data_ptr(), n, V, ignore_index,
+                                      out.data_ptr(), _stream()), "vb_cross_entropy")
+    return out

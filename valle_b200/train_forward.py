@@ -1,0 +1,188 @@
+"""VALLE.forward (training loss, valle/models/valle.py:762-959) on the sm_100a kernels.
+
+Forward only (no autograd graph): embeddings + sine PE, the AR stack over padded
+[text | audio] rows with the merged causal/key-padding rule, one NAR stage with AdaLN, the
+prediction heads (tensor-core GEMMs in bf16 mode), cross-entropy and top-10 accuracy.  Used for
+validation / scoring from bin/trainer.py; the backward pass is listed under "next" in DESIGN.md,
+so calling it in training mode raises instead of silently skipping dropout.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple, Union
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+from . import ops
+from .models.macros import NUM_AUDIO_TOKENS
+
+
+def _make_pad_mask(lengths: torch.Tensor, max_len: int = 0) -> torch.Tensor:
+    """icefall.utils.make_pad_mask as called at valle.py:804-805."""
+    max_len = max(max_len, int(lengths.max()))
+    return torch.arange(max_len, device=lengths.device)[None, :] >= lengths[:, None]
+
+
+def _top10(logits: torch.Tensor, targets: torch.Tensor, ignore: int) -> torch.Tensor:
+    """MulticlassAccuracy(top_k=10, average="micro", ignore_index=ignore) (valle.py:157-163)."""
+    keep = targets != ignore
+    hit = (logits.topk(10, dim=-1).indices == targets[:, None]).any(-1) & keep
+    return hit.sum().float() / keep.sum().clamp(min=1).float()
+
+
+@torch.no_grad()
+def valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, reduction: str = "sum",
+                  train_stage: int = 0, **kwargs):
+    from .models.valle import PromptedFeatures
+    if model.training:
+        raise NotImplementedError("valle_b200.VALLE.forward: forward-only (eval mode); the backward pass / "
+                                  "training-mode dropout is not built -- call model.eval()")
+    assert x.ndim == 2, x.shape
+    assert x_lens.ndim == 1, x_lens.shape
+    y_prompts_codes = None
+    if isinstance(y, PromptedFeatures):
+        y_prompts_codes, y = y.data
+        prompts_len, y_lens = y_lens.data
+        assert prompts_len.min() == prompts_len.max()
+        assert model.prefix_mode == 4
+        y_prompts_codes = y_prompts_codes.type(torch.int64)
+    assert y.ndim == 3, y.shape
+    assert y_lens.ndim == 1, y_lens.shape
+    assert reduction == "sum", "only reduction='sum' (the trainer's setting) is built"
+    dev = model.ar_predict_layer.weight.device
+    if dev.type != "cuda":
+        raise L.VbError("valle_b200: the model must live on a CUDA device (no CPU fallback)")
+    dtype = model.engine_dtype
+    x, y = x.to(dev), y.to(dev)
+    x_lens, y_lens = x_lens.to(dev), y_lens.to(dev)
+    N, d, Q = x.shape[0], model.ar_predict_layer.weight.shape[1], model.num_quantizers
+    x_mask = _make_pad_mask(x_lens)
+    y_mask = _make_pad_mask(y_lens)
+    y_mask_int = y_mask.type(torch.int64)
+    text = x.to(torch.int64).contiguous()
+    codes = (y.type(torch.int64) * (1 - y_mask_int.unsqueeze(dim=-1))).contiguous()
+    yin, targets = model.pad_y_eos(codes[..., 0], y_mask_int, eos_id=NUM_AUDIO_TOKENS)
+    Smax, Tmax = int(x_lens.max()), int(y_lens.max())
+    xl32, yl32 = x_lens.to(torch.int32).contiguous(), y_lens.to(torch.int32).contiguous()
+    metrics: Dict[str, torch.Tensor] = {}
+    total_loss = torch.zeros((), device=dev)
+    x_emb_out = None
+
+    def embed_pe(tokens, table, pos_mod, T):
+        """[N, T] ids -> [N, T, d] = table[ids] + alpha * pe[:T]."""
+        tok = tokens.reshape(-1).contiguous()
+        e = torch.empty((tok.numel(), d), dtype=torch.float32, device=dev)
+        ops.embed_sum(tok, 1, 0, [table.detach()], tok.numel(), e)
+        pe = pos_mod.table(T, dev)
+        e = e.view(N, T, d)
+        out = torch.empty_like(e)
+        for b in range(N):
+            ops.add_pe(e[b], pe, pos_mod.alpha.detach(), out[b], T, pos0=0)
+        return out
+
+    def stack(nd, rows, seg1_lens, mode, ada=None, Lp=None):
+        cu = (torch.arange(N + 1, dtype=torch.int32, device=dev) * Lp).contiguous()
+        nd.forward(rows, cu, N, Lp, mode, xl32, ada, seg1_lens=seg1_lens, seg1_start=Smax)
+        return rows
+
+    # ---- AR decoder (valle.py:828-881) ----
+    if train_stage in (0, 1):
+        xe = embed_pe(text, model.ar_text_embedding.weight, model.ar_text_position, Smax)
+        ye = embed_pe(yin.contiguous(), model.ar_audio_embedding.weight, model.ar_audio_position, Tmax)
+        rows = torch.cat([xe, ye], dim=1).reshape(N * (Smax + Tmax), d).contiguous()
+        nd = model.ar_decoder.native(dtype)
+        stack(nd, rows, yl32, L.VB_MASK_PADDED_AR, None, Smax + Tmax)
+        sel = (torch.arange(N, device=dev)[:, None] * (Smax + Tmax) + Smax
+               + torch.arange(Tmax, device=dev)[None, :]).reshape(-1).to(torch.int32).contiguous()
+        hn = nd.final_norm(rows, None, rows=sel, out_dtype=dtype)
+        w = model.ar_predict_layer.weight.detach()
+        logits = ops.linear(hn, w if dtype == torch.float32 else w.to(dtype), None, out_dtype=torch.float32)
+        tg = targets.reshape(-1).contiguous()
+        total_loss = total_loss + ops.cross_entropy_rows(logits, tg).sum()
+        metrics["ArTop10Accuracy"] = _top10(logits, tg, NUM_AUDIO_TOKENS).item() * y_lens.sum().type(torch.float32)
+        x_emb_out = xe
+
+    if Q == 1:
+        return ((x_emb_out, codes), total_loss, metrics)
+
+    # ---- NAR decoder, one random stage (valle.py:886-954) ----
+    if train_stage in (0, 2):
+        num_nar_layers = Q - 1
+        nar_stage = model.rng.choices([_k for _k in range(1, Q)], weights=[1.0 / num_nar_layers] * num_nar_layers, k=1)[0]
+        xe = embed_pe(text, model.nar_text_embedding.weight, model.nar_text_position, Smax)
+        emb = [e.weight.detach() for e in model.nar_audio_embeddings]
+        yq = codes[..., 0].contiguous()
+        pm = model.prefix_mode
+
+        def emb_sum(tok2d, tabs, T):  # [N, T, len(tabs)] ids -> sum_j tabs[j][ids[..., j]] in order
+            tok = tok2d.reshape(-1, len(tabs)).contiguous()
+            o = torch.empty((tok.shape[0], d), dtype=torch.float32, device=dev)
+            ops.embed_sum(tok, len(tabs), 1, tabs, tok.shape[0], o)
+            return o.view(N, T, d)
+
+        if pm == 0:  # valle.py:339-345
+            prefix_len = 0
+            y_emb = emb_sum(codes[..., :nar_stage], emb[:nar_stage], Tmax)
+        elif pm == 1:  # valle.py:346-362
+            int_low = (0.25 * y_lens.min()).type(torch.int64).item()
+            prefix_len = torch.randint(int_low, int_low * 2, size=()).item()
+            prefix_len = min(prefix_len, 225)
+            y_prompts = emb_sum(codes[:, :prefix_len], emb[:Q], prefix_len)
+            y_rest = emb_sum(codes[:, prefix_len:, :nar_stage], emb[:nar_stage], Tmax - prefix_len)
+            y_emb = torch.cat([y_prompts, y_rest], dim=1)
+        elif pm in (2, 4):  # valle.py:363-389
+            if pm == 2:
+                prefix_len = min(225, int(0.25 * y_lens.min().item()))
+                pcs = []
+                for b in range(N):
+                    start = model.rng.randint(0, y_lens[b].item() - prefix_len)
+                    pcs.append(torch.clone(codes[b, start:start + prefix_len]))
+                    codes[b, start:start + prefix_len, nar_stage] = NUM_AUDIO_TOKENS
+                y_prompts_codes = torch.stack(pcs, dim=0)
+            else:
+                prefix_len = y_prompts_codes.shape[1]
+                y_prompts_codes = y_prompts_codes.to(dev)
+            y_prompts = emb_sum(y_prompts_codes, emb[:Q], prefix_len)
+            y_rest = emb_sum(codes[..., :nar_stage], emb[:nar_stage], Tmax)
+            y_emb = torch.cat([y_prompts, y_rest], dim=1)
+        else:
+            raise ValueError
+        tg = codes[..., nar_stage] + NUM_AUDIO_TOKENS * y_mask_int
+        Ty = y_emb.shape[1]
+        seg1 = yl32
+        if pm in (2, 4):
+            seg1 = (yl32 + (Ty - Tmax)).contiguous()   # key mask F.pad(y_mask, (prefix, 0), False) valle.py:908-914
+        elif pm == 1:
+            tg = tg[:, prefix_len:]
+        pe = model.nar_audio_position.table(Ty, dev)
+        y_pos = torch.empty((N, Ty, d), dtype=torch.float32, device=dev)
+        y_emb = y_emb.contiguous()
+        for b in range(N):
+            ops.add_pe(y_emb[b], pe, model.nar_audio_position.alpha.detach(), y_pos[b], Ty, pos0=0)
+        Lp = Smax + Ty
+        rows = torch.cat([xe, y_pos], dim=1).reshape(N * Lp, d).contiguous()
+        nd = model.nar_decoder.native(dtype)
+        ada = nd.ada_table(model.nar_stage_embeddings[nar_stage - 1].weight)
+        stack(nd, rows, seg1, L.VB_MASK_PADDED, ada, Lp)
+        off = Smax + prefix_len
+        if pm == 4:
+            off = Smax + prefix_len
+        Tt = Lp - off
+        sel = (torch.arange(N, device=dev)[:, None] * Lp + off
+               + torch.arange(Tt, device=dev)[None, :]).reshape(-1).to(torch.int32).contiguous()
+        hn = nd.final_norm(rows, ada, rows=sel, out_dtype=dtype)
+        w = model.nar_predict_layers[nar_stage - 1].weight.detach()
+        logits = ops.linear(hn, w if dtype == torch.float32 else w.to(dtype), None, out_dtype=torch.float32)
+        tgf = tg.reshape(-1).contiguous()
+        if pm == 4:
+            prefix_len = 0  # reset for the metric / loss rescale (valle.py:927-928)
+        total_length = y_lens.sum().type(torch.float32)
+        ce = ops.cross_entropy_rows(logits, tgf, ignore_index=NUM_AUDIO_TOKENS).sum()
+        total_loss = total_loss + ce * (total_length / (total_length - prefix_len * N))
+        lp = F.pad(logits, (0, 1), value=logits.min().item())   # valle.py:946-950
+        metrics["NarTop10Accuracy"] = _top10(lp, tgf, NUM_AUDIO_TOKENS).item() * total_length
+        x_emb_out = xe
+    if train_stage == 0:
+        total_loss = total_loss / 2.0
+    return ((x_emb_out, codes), total_loss, metrics)
