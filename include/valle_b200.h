@@ -223,6 +223,33 @@ int vb_cross_entropy(const float *logits, int64_t ld_logits, const int64_t *targ
 int vb_gather_rows(const float *src, int64_t src_row_stride, const int32_t *rows, int64_t n_rows,
                    int d, float *dst, int64_t dst_row_stride, vb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * a13  AudioTokenizer.encode / .decode (valle/data/tokenizer.py:211-254) -> PyPI `encodec`
+ *      EncodecModel.encodec_model_24khz() at 6 kbps: SEANet conv stacks, 2-layer LSTM, 8-stage RVQ.
+ *      fp32, activations [B, C, T] (time contiguous).
+ * ---------------------------------------------------------------------------------------- */
+/* SConv1d: y = conv1d(pad(act(x))) + bias (+ residual); act = ELU if pre_elu; padding (pad_left,
+ * pad_right) reflect or zero; w [Cout, Cin, K] (weight-norm already folded, tokenizer.py:181-208). */
+int vb_conv1d(const float *x, int B, int Cin, int Tin, const float *w, const float *bias, int Cout, int K,
+              int stride, int dilation, int pad_left, int pad_right, int reflect, int pre_elu,
+              const float *residual, float *out, int Tout, vb_stream_t stream);
+/* causal SConvTranspose1d with K == 2*stride, right padding trimmed: out [B, Cout, Tin*stride];
+ * w [Cin, Cout, K] */
+int vb_conv_transpose1d(const float *x, int B, int Cin, int Tin, const float *w, const float *bias, int Cout,
+                        int K, int stride, int pre_elu, float *out, vb_stream_t stream);
+/* one LSTM layer over T steps: xproj [T, B, 4H] = W_ih x + b_ih + b_hh (gate order i,f,g,o),
+ * whh_t [H, 4H] = W_hh^T, h_seq [T, B, H] out, c_state [B, H] scratch */
+int vb_lstm_layer(const float *xproj, const float *whh_t, int T, int B, int H, float *h_seq, float *c_state,
+                  vb_stream_t stream);
+/* residual VQ encode of rows x [n_rows, dim]: per stage idx = argmax -(|r|^2 - 2 r.e + |e|^2), r -= e_idx.
+ * codebooks [n_q, n_codes, dim], codebooks_t [n_q, dim, n_codes], codebook_sq [n_q, n_codes];
+ * codes[row*code_row_stride + q*code_q_stride] (int64) */
+int vb_rvq_encode(const float *x, int64_t n_rows, int dim, int n_q, int n_codes, const float *codebooks,
+                  const float *codebooks_t, const float *codebook_sq, int64_t *codes, int64_t code_row_stride,
+                  int64_t code_q_stride, vb_stream_t stream);
+/* out = in.permute(p0, p1, p2) for a contiguous [d0, d1, d2] fp32 tensor */
+int vb_permute3(const float *in, int d0, int d1, int d2, int p0, int p1, int p2, float *out, vb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

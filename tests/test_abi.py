@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert os.path.exists(path)
     lib = ctypes.CDLL(path)
     syms = header_symbols()
-    assert len(syms) >= 19
+    assert len(syms) >= 25
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/valle_b200.h but not exported"
     assert set(_lib.PROTOTYPES) == set(syms), set(_lib.PROTOTYPES) ^ set(syms)
