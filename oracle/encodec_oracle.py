@@ -20,10 +20,19 @@ def build_codec(seed: int = 0):
     torch.manual_seed(seed)
     m = EncodecModel(EncodecConfig()).eval()
     g = torch.Generator().manual_seed(seed + 1)
-    # codebooks at the scale of the (random-weight) encoder output, shrinking per stage like residuals
-    # do -- otherwise one minimum-norm code wins every frame and the comparison is vacuous
-    for q, layer in enumerate(m.quantizer.layers):
-        layer.codebook.embed.copy_(torch.randn(layer.codebook.embed.shape, generator=g) * (0.03 * 0.75 ** q))
+    # Codebooks placed where the (random-weight) encoder output actually lives: stage 0 around the
+    # per-dimension mean/std of the embeddings of a calibration signal, later stages zero-mean with a
+    # shrinking scale like real residuals -- otherwise one code wins every frame and the check is vacuous.
+    with torch.no_grad():
+        cal = (torch.randn(2, 1, 24000, generator=g) * 0.3).clamp(-1, 1)
+        emb = m.encoder(cal)                                   # [2, 128, 75]
+        mu = emb.mean(dim=(0, 2))
+        sd = emb.std(dim=(0, 2)) + 1e-6
+        for q, layer in enumerate(m.quantizer.layers):
+            e = torch.randn(layer.codebook.embed.shape, generator=g) * sd * (0.8 ** q)
+            if q == 0:
+                e = e + mu
+            layer.codebook.embed.copy_(e)
     return m
 
 

@@ -420,7 +420,11 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
   float *part_ml = part_o + (size_t)B * n_head * ns * HD;
   QkvPartials qp{qkv_part, qkv_bias, qkv_splits, qkv_ldp};
   dim3 grid(n_head, B, ns);
-  if (dtype == VB_F32)
+  if (dtype == VB_BF16 && getenv("VB_ATTN_DECODE_SIMPLE") == nullptr)
+    VB_TRY(launch_attn_decode_tma(q, qkv_part, qkv_splits, qkv_ldp, qkv_bias, B, n_head, kcache, vcache,
+                                  cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out, out16, part_o, part_ml,
+                                  ns, pdl, s));
+  else if (dtype == VB_F32)
     VB_CUDA(launch_kernel(attn_decode_kernel<float>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (float *)kcache,
                           (float *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
                           (bf16 *)out16, part_o, part_ml, ns));
