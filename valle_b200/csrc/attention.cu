@@ -185,6 +185,9 @@ int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_
     VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, 256, smem, s>>>((const float *)qkv, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, (float *)out,
                               (float *)kcache, (float *)vcache, cache_seq_stride, cache_cap);
+  } else if (dtype == VB_BF16 && kcache == nullptr && getenv("VB_ATTN_SIMT") == nullptr && attention_tcgen05_enabled()) {
+    return launch_attention_tcgen05((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start,
+                                    max_seqlen, mask_mode, (bf16 *)out, s);
   } else if (dtype == VB_BF16 && getenv("VB_ATTN_SIMT") == nullptr) {
     return launch_attention_mma((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, max_seqlen, mask_mode,
                                 (bf16 *)out, (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, s);
@@ -230,9 +233,155 @@ struct QkvPartials {
   int splits, ldp;
 };
 
+// Single pass, no block-level synchronisation inside the loop: each 8-lane group owns every 16th key of
+// the chunk, streams the K row and the V row of its keys together (4 keys = 8 x 16-byte loads in
+// flight per lane), and keeps its OWN online-softmax state (m, l, 8 output elements per lane).  The 16
+// groups are merged once at the end (flash-decoding style).
 template <typename T>
 __global__ void __launch_bounds__(128)
 attn_decode_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *__restrict__ kcache,
+                   T *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
+                   const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
+                   const int32_t *__restrict__ n_gen, float *__restrict__ out, bf16 *__restrict__ out16,
+                   float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit) {
+  __shared__ __align__(16) float qs[HD];
+  __shared__ __align__(16) float knew[HD];
+  __shared__ __align__(16) float vnew[HD];
+  __shared__ float g_o[16][HD + 1];
+  __shared__ float g_m[16], g_l[16];
+  pdl_launch_dependents();
+  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = n_head * HD;
+  pdl_wait();
+  int kv_len = text_len[b] + prompt_len[b] + n_gen[b];
+  kv_len = max(1, min(kv_len, cache_cap));
+  const int pos = kv_len - 1;  // cache row of the current token
+  const int chunk = ((kv_len + nsplit - 1) / nsplit + 15) & ~15;
+  const int c0 = sp * chunk, c1 = min(kv_len, c0 + chunk);
+  const int n = max(0, c1 - c0);
+  T *kb = kcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
+  T *vb_ = vcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
+  const bool has_new = qp.part != nullptr;
+  if (tid < HD) {
+    if (has_new) {
+      float a[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int col = j * d + h * HD + tid;
+        const float *p = qp.part + (int64_t)b * qp.ldp + col;
+        float acc = __ldcg(p);
+#pragma unroll 6
+        for (int s = 1; s < qp.splits; ++s) acc += __ldcg(p + (int64_t)s * 64 * qp.ldp);
+        a[j] = acc + qp.bias[col];
+      }
+      qs[tid] = a[0] * 0.125f;
+      const T k16 = from_f32<T>(a[1]), v16 = from_f32<T>(a[2]);
+      knew[tid] = to_f32(k16);  // exactly what later steps will read back from the cache
+      vnew[tid] = to_f32(v16);
+      if (sp == 0) {
+        kb[(int64_t)pos * HD + tid] = k16;
+        vb_[(int64_t)pos * HD + tid] = v16;
+      }
+    } else {
+      qs[tid] = q[(int64_t)b * d + h * HD + tid] * 0.125f;
+    }
+  }
+  __syncthreads();
+
+  const int grp = warp * 4 + (lane >> 3);  // 0..15
+  const int j8 = (lane & 7) * 8;           // this lane's 8 head dims
+  float qf[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qf[i] = qs[j8 + i];
+  float m = -CUDART_INF_F, l = 0.f, acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+
+  for (int base = 0; base < n; base += 64) {
+    float kf[4][8], vf[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = base + u * 16 + grp;
+      const int kk = min(key, n - 1);
+      KvRow8<T>::load(kb + (int64_t)(c0 + kk) * HD + j8, kf[u]);
+      KvRow8<T>::load(vb_ + (int64_t)(c0 + kk) * HD + j8, vf[u]);
+    }
+    float s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int key = base + u * 16 + grp;
+      if (has_new && c0 + min(key, n - 1) == pos) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          kf[u][i] = knew[j8 + i];
+          vf[u][i] = vnew[j8 + i];
+        }
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], kf[u][i], dot);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+      s[u] = key < n ? dot : -CUDART_INF_F;
+    }
+    const float mt = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3]));
+    const float mn = fmaxf(m, mt);  // finite: key `base + grp` < n whenever this group has work ...
+    if (mn != -CUDART_INF_F) {      // ... otherwise the group has no key in this tile at all
+      const float corr = expf(m - mn);
+      float p[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) p[u] = expf(s[u] - mn);
+      l = l * corr + ((p[0] + p[1]) + (p[2] + p[3]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = acc[i] * corr;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a = fmaf(p[u], vf[u][i], a);
+        acc[i] = a;
+      }
+      m = mn;
+    }
+  }
+  // ---- merge the 16 groups ------------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g_o[grp][j8 + i] = acc[i];
+  if ((lane & 7) == 0) {
+    g_m[grp] = m;
+    g_l[grp] = l;
+  }
+  __syncthreads();
+  if (tid < HD) {
+    float mm = -CUDART_INF_F;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) mm = fmaxf(mm, g_m[g]);
+    float lt = 0.f, ot = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) {
+      if (g_m[g] == -CUDART_INF_F) continue;
+      const float w = expf(g_m[g] - mm);
+      lt += g_l[g] * w;
+      ot += g_o[g][tid] * w;
+    }
+    if (nsplit == 1) {
+      out[(int64_t)b * d + h * HD + tid] = ot / lt;
+      if (out16) out16[(int64_t)b * d + h * HD + tid] = __float2bfloat16_rn(ot / lt);
+    } else {
+      const int64_t pi = ((int64_t)b * n_head + h) * nsplit + sp;
+      part_o[pi * HD + tid] = ot;
+      if (tid == 0) {
+        part_ml[pi * 2] = n > 0 ? mm : -CUDART_INF_F;
+        part_ml[pi * 2 + 1] = n > 0 ? lt : 0.f;
+      }
+    }
+  }
+}
+
+// two-phase variant (scores of the whole chunk to shared memory, block softmax, then P.V)
+template <typename T>
+__global__ void __launch_bounds__(128)
+attn_decode_2phase_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *__restrict__ kcache,
                    T *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
                    const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
                    const int32_t *__restrict__ n_gen, float *__restrict__ out, bf16 *__restrict__ out16,
@@ -397,6 +546,8 @@ __global__ void attn_decode_combine_kernel(const float *__restrict__ part_o,
 }
 
 static int decode_nsplit(int B, int n_head, int cache_cap) {
+  static const int forced = getenv("VB_DECODE_NSPLIT") ? atoi(getenv("VB_DECODE_NSPLIT")) : 0;
+  if (forced > 0) return forced;
   int ns = (2 * sm_count() + B * n_head - 1) / (B * n_head);
   ns = max(1, min(ns, 32));
   ns = min(ns, max(1, cache_cap / 64));              // keep chunks >= 64 keys
@@ -420,13 +571,17 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
   float *part_ml = part_o + (size_t)B * n_head * ns * HD;
   QkvPartials qp{qkv_part, qkv_bias, qkv_splits, qkv_ldp};
   dim3 grid(n_head, B, ns);
-  if (dtype == VB_BF16 && getenv("VB_ATTN_DECODE_SIMPLE") == nullptr)
+  if (dtype == VB_BF16 && getenv("VB_ATTN_DECODE_TMA") != nullptr)  // opt-in: cp.async.bulk ring variant
     VB_TRY(launch_attn_decode_tma(q, qkv_part, qkv_splits, qkv_ldp, qkv_bias, B, n_head, kcache, vcache,
                                   cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out, out16, part_o, part_ml,
                                   ns, pdl, s));
   else if (dtype == VB_F32)
     VB_CUDA(launch_kernel(attn_decode_kernel<float>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (float *)kcache,
                           (float *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
+                          (bf16 *)out16, part_o, part_ml, ns));
+  else if (getenv("VB_ATTN_DECODE_1PASS") == nullptr)
+    VB_CUDA(launch_kernel(attn_decode_2phase_kernel<bf16>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
+                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
                           (bf16 *)out16, part_o, part_ml, ns));
   else
     VB_CUDA(launch_kernel(attn_decode_kernel<bf16>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,

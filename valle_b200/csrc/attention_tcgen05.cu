@@ -1,0 +1,320 @@
+// bf16 flash attention on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), head_dim 64, packed
+// ragged sequences -- the L x L attention of the 7 NAR passes and of the training forward
+// (F.multi_head_attention_forward, valle/modules/activation.py:408-427; no mask for NAR
+// valle/models/valle.py:1125-1127, key-padding / causal rules of valle.py:835-861,921-925).
+//
+// One CTA = 128 query rows of one (sequence, head); 192 threads:
+//   warp 0    TMA producer: Q tile once, then K and V tiles (128 keys x 64, 128B-swizzle boxes of the
+//             packed [M, 3d] qkv matrix) through a 2-stage mbarrier ring
+//   warp 1    MMA issuer:  S = Q K^T  (tcgen05.mma M=128, N=128, K=16 x4, fp32 in TMEM columns 0..127)
+//                          O_t = P V   (M=128, N=64, K=16 x8, TMEM columns 128..191; P from shared
+//                          memory as the K-major A operand, V as an MN-major B operand -- the V tile
+//                          is used exactly as TMA lands it, no transpose)
+//   warps 2-5 softmax: ONE THREAD OWNS ONE QUERY ROW (TMEM lane): row max / sum without shuffles,
+//             p = exp2(s*c - m) -> bf16 -> swizzled shared memory (A operand of P V); after the P V MMA
+//             the thread folds O_t into its fp32 accumulator row with the online-softmax correction.
+// QK^T of tile j+1 is issued right after P V of tile j, so the tensor pipe works while the softmax
+// threads fold O_t; two CTAs fit per SM (112 KB smem, 256 TMEM columns each) and interleave.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tcgen05_ptx.cuh"
+
+namespace vb {
+namespace fa5 {
+
+using namespace tc;
+
+constexpr int HD = 64, BQ = 128, BKV = 128;
+constexpr int kThreads = 192;
+constexpr int kQBytes = BQ * HD * 2;         // 16 KB
+constexpr int kKBytes = BKV * HD * 2;        // 16 KB
+constexpr int kStageBytes = 2 * kKBytes;     // K + V
+constexpr int kStages = 2;
+constexpr int kPBytes = BQ * BKV * 2;        // 32 KB (two 64-key K-blocks of [128 x 64])
+constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kPBytes + 256;  // 2 CTAs per SM must fit
+constexpr int kTmemCols = 256;               // S: 128 cols, O_t: 64 cols
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// MN-major, 128-byte swizzle descriptor: a [K rows x 64 MN] tile stored as rows of 128 bytes
+// (8 rows = one 1024-byte swizzle atom).  SBO = 1024 B between 8-row groups along K.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 16;  // leading byte offset (MN direction, unused for N = 64)
+  d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset (K direction)
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor with B MN-major (bit 16)
+__host__ __device__ constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }
+
+__global__ void __launch_bounds__(kThreads, 2)
+attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const int32_t *__restrict__ cu_seqlens,
+                    const int32_t *__restrict__ text_lens, const int32_t *__restrict__ seg1_lens, int seg1_start,
+                    int mask_mode, bf16 *__restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t *sQ = smem;
+  uint8_t *sKV = sQ + kQBytes;                       // [stage][K | V]
+  uint8_t *sP = sKV + kStages * kStageBytes;         // [2 k-blocks][128 rows x 128 B]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + kPBytes);
+  uint64_t *q_full = bars;              // 1
+  uint64_t *kv_full = bars + 1;         // [kStages]
+  uint64_t *kv_empty = kv_full + kStages;
+  uint64_t *s_full = kv_empty + kStages;   // S ready in TMEM
+  uint64_t *p_full = s_full + 1;           // P in smem, S consumed (4 warp arrivals)
+  uint64_t *o_full = p_full + 1;           // O_t ready in TMEM
+  uint64_t *o_empty = o_full + 1;          // O_t consumed, P buffer free (4 warp arrivals)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 1);
+
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int r0 = cu_seqlens[b], L = cu_seqlens[b + 1] - r0;
+  const int q0 = blockIdx.x * BQ;
+  if (q0 >= L) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = n_head * HD;
+  const int S = (mask_mode != VB_MASK_FULL) ? text_lens[b] : 0;
+  const int c1 = (mask_mode >= VB_MASK_PADDED_AR) ? seg1_lens[b] : 0;
+  const int q_hi = min(q0 + BQ, L);
+  const int kv_max = (mask_mode == VB_MASK_VALLE_AR) ? max(S, q_hi) : L;
+  const int n_tiles = (kv_max + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(q_full, kQBytes);
+      tma_load_2d(&tmap, q_full, sQ, h * HD, r0 + q0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t *dst = sKV + stage * kStageBytes;
+        mbar_expect_tx(&kv_full[stage], kStageBytes);
+        tma_load_2d(&tmap, &kv_full[stage], dst, d + h * HD, r0 + t * BKV);
+        tma_load_2d(&tmap, &kv_full[stage], dst + kKBytes, 2 * d + h * HD, r0 + t * BKV);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(BQ, BKV);      // S = Q K^T : both K-major
+      constexpr uint32_t idesc_o = make_idesc_bmn(BQ, HD);   // O_t = P V : A K-major, B MN-major
+      const uint64_t qdesc = make_smem_desc(smem_u32(sQ));
+      const uint64_t pdesc0 = make_smem_desc(smem_u32(sP));
+      mbar_wait(q_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      // prologue: S(0)
+      mbar_wait(&kv_full[0], 0);
+      tcgen05_fence_after();
+      {
+        const uint64_t kdesc = make_smem_desc(smem_u32(sKV));
+#pragma unroll
+        for (int k = 0; k < HD / UMMA_K; ++k) umma_bf16(tmem_s, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
+        tcgen05_commit(s_full);
+      }
+      for (int t = 0; t < n_tiles; ++t) {
+        // ---- O_t = P(t) V(t) ----
+        mbar_wait(p_full, t & 1);                 // P(t) written, S(t) consumed
+        if (t > 0) mbar_wait(o_empty, (t - 1) & 1);  // O_t(t-1) folded
+        tcgen05_fence_after();
+        const uint32_t v_addr = smem_u32(sKV + stage * kStageBytes + kKBytes);
+        const uint64_t vdesc = make_smem_desc_mn(v_addr);
+#pragma unroll
+        for (int k = 0; k < BKV / UMMA_K; ++k) {
+          // A: P k-block (k / 4), +32 B per 16 keys inside the 64-key swizzle atom
+          const uint64_t pd = pdesc0 + (uint64_t)((k >> 2) * (kQBytes >> 4)) + (uint64_t)((k & 3) * 2);
+          // B: V rows 16k .. 16k+15 = two 1024-byte atoms per k-step
+          const uint64_t vd = vdesc + (uint64_t)(k * (2048 >> 4));
+          umma_bf16(tmem_o, pd, vd, idesc_o, k != 0);
+        }
+        tcgen05_commit(o_full);
+        tcgen05_commit(&kv_empty[stage]);  // K(t), V(t) free once these MMAs retire
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        // ---- S(t+1) = Q K(t+1)^T, overlapping the softmax threads' fold of O_t(t) ----
+        if (t + 1 < n_tiles) {
+          mbar_wait(&kv_full[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t kdesc = make_smem_desc(smem_u32(sKV + stage * kStageBytes));
+#pragma unroll
+          for (int k = 0; k < HD / UMMA_K; ++k) umma_bf16(tmem_s, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
+          tcgen05_commit(s_full);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax: thread = one query row =====
+    const int quarter = warp & 3;                  // TMEM lanes this warp may touch
+    const int row = quarter * 32 + lane;           // row within the tile
+    const int qr = q0 + row;
+    const RowMask rm = make_row_mask(mask_mode, qr, L, S, seg1_start, c1);
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    float acc[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    float m = -CUDART_INF_F, l = 0.f;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int j0 = t * BKV;
+      mbar_wait(s_full, t & 1);
+      tcgen05_fence_after();
+      // pass 1: row maximum
+      float mx = -CUDART_INF_F;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BKV; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + lane_off + c0, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (rm.ok(j0 + c0 + i)) mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+      const float m_new = fmaxf(m, mx * sc);
+      const float m_use = m_new == -CUDART_INF_F ? 0.f : m_new;
+      const float corr = ex2(m - m_use);
+      // previous P V must have consumed the P buffer before it is overwritten
+      if (t > 0) {
+        mbar_wait(o_full, (t - 1) & 1);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < HD; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_o + lane_off + c0, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);
+      }
+      // rescale the accumulator for the new maximum
+#pragma unroll
+      for (int i = 0; i < HD; ++i) acc[i] *= corr;
+      l *= corr;
+      m = m_new;
+      // pass 2: p = 2^(s*c - m) -> bf16 -> swizzled shared memory
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BKV; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + lane_off + c0, r);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = rm.ok(j0 + c0 + i) ? ex2(__uint_as_float(r[i]) * sc - m_use) : 0.f;
+          const float p1 = rm.ok(j0 + c0 + i + 1) ? ex2(__uint_as_float(r[i + 1]) * sc - m_use) : 0.f;
+          rs += p0 + p1;
+          __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
+          pk[i >> 1] = *reinterpret_cast<uint32_t *>(&pp);
+        }
+        // 32 keys = 4 chunks of 16 B in k-block (c0 / 64), chunk index ((c0 % 64) / 8 + j)
+        uint8_t *blk = sP + (c0 >> 6) * kQBytes + row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = ((c0 & 63) >> 3) + j;
+          *reinterpret_cast<uint4 *>(blk + ((chunk ^ (row & 7)) << 4)) =
+              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+      }
+      l += rs;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P visible to the tensor-core proxy
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // last O_t
+    mbar_wait(o_full, (n_tiles - 1) & 1);
+    tcgen05_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_o + lane_off + c0, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+    }
+    if (qr < L) {
+      const float inv = 1.f / l;
+      uint4 *dst = reinterpret_cast<uint4 *>(out + (int64_t)(r0 + qr) * d + h * HD);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __nv_bfloat162 a0 = __floats2bfloat162_rn(acc[8 * j] * inv, acc[8 * j + 1] * inv);
+        __nv_bfloat162 a1 = __floats2bfloat162_rn(acc[8 * j + 2] * inv, acc[8 * j + 3] * inv);
+        __nv_bfloat162 a2 = __floats2bfloat162_rn(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv);
+        __nv_bfloat162 a3 = __floats2bfloat162_rn(acc[8 * j + 6] * inv, acc[8 * j + 7] * inv);
+        dst[j] = make_uint4(*reinterpret_cast<uint32_t *>(&a0), *reinterpret_cast<uint32_t *>(&a1),
+                            *reinterpret_cast<uint32_t *>(&a2), *reinterpret_cast<uint32_t *>(&a3));
+      }
+    }
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+}  // namespace fa5
+
+bool attention_tcgen05_enabled() { return getenv("VB_ATTN_MMA_SYNC") == nullptr; }
+
+int launch_attention_tcgen05(const bf16 *qkv, int64_t M, int B, int n_head, const int32_t *cu_seqlens,
+                             const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
+                             int mask_mode, bf16 *out, cudaStream_t s) {
+  if (M == 0 || B == 0) return VB_OK;
+  const int d = n_head * fa5::HD;
+  CUtensorMap tm;
+  VB_TRY(tc::make_tmap(&tm, qkv, M, 3 * d, 3 * (int64_t)d, fa5::BQ));
+  static bool attr = false;
+  if (!attr) {
+    VB_CUDA(cudaFuncSetAttribute(fa5::attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa5::kSmemBytes));
+    attr = true;
+  }
+  dim3 grid((max_seqlen + fa5::BQ - 1) / fa5::BQ, n_head, B);
+  fa5::attn_tcgen05_kernel<<<grid, fa5::kThreads, fa5::kSmemBytes, s>>>(tm, n_head, cu_seqlens, text_lens, seg1_lens,
+                                                                      seg1_start, mask_mode, out);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+}  // namespace vb
