@@ -55,6 +55,60 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
 // instruction descriptor with B MN-major (bit 16)
 __host__ __device__ constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }
 
+// row maximum of the raw scores of one 128-key tile (thread = TMEM lane)
+template <bool kMask>
+__device__ __forceinline__ float tile_row_max(uint32_t taddr, const RowMask &rm, int j0) {
+  float mx = -CUDART_INF_F;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BKV; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c0, r);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (kMask) {
+        if (rm.ok(j0 + c0 + i)) mx = fmaxf(mx, __uint_as_float(r[i]));
+      } else {
+        mx = fmaxf(mx, __uint_as_float(r[i]));
+      }
+    }
+  }
+  return mx;
+}
+// p = 2^(s*c - m) -> bf16 -> swizzled shared memory (K-major A operand of P V); returns the row sum
+template <bool kMask>
+__device__ __forceinline__ float tile_row_p(uint32_t taddr, const RowMask &rm, int j0, float sc, float m_use,
+                                            uint8_t *sP, int row) {
+  float rs = 0.f;
+  const float nm = -m_use;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BKV; c0 += 32) {
+    uint32_t r[32];
+    tmem_ld32(taddr + c0, r);
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float p0 = ex2(fmaf(__uint_as_float(r[i]), sc, nm));
+      float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), sc, nm));
+      if (kMask) {
+        if (!rm.ok(j0 + c0 + i)) p0 = 0.f;
+        if (!rm.ok(j0 + c0 + i + 1)) p1 = 0.f;
+      }
+      rs += p0 + p1;
+      __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
+      pk[i >> 1] = *reinterpret_cast<uint32_t *>(&pp);
+    }
+    // 32 keys = 4 chunks of 16 B in k-block (c0 / 64), chunk index ((c0 % 64) / 8 + j)
+    uint8_t *blk = sP + (c0 >> 6) * kQBytes + row * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int chunk = ((c0 & 63) >> 3) + j;
+      *reinterpret_cast<uint4 *>(blk + ((chunk ^ (row & 7)) << 4)) =
+          make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    }
+  }
+  return rs;
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const int32_t *__restrict__ cu_seqlens,
                     const int32_t *__restrict__ text_lens, const int32_t *__restrict__ seg1_lens, int seg1_start,
@@ -198,16 +252,11 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
       const int j0 = t * BKV;
       mbar_wait(s_full, t & 1);
       tcgen05_fence_after();
-      // pass 1: row maximum
-      float mx = -CUDART_INF_F;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_s + lane_off + c0, r);
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (rm.ok(j0 + c0 + i)) mx = fmaxf(mx, __uint_as_float(r[i]));
-      }
+      // interior tile: every key of the tile is visible to this row -> no per-element mask
+      // (warp-uniform: tcgen05.ld is .sync.aligned, a diverged warp must never reach it)
+      const bool interior = __all_sync(0xffffffffu, j0 + BKV <= rm.lim0);
+      const float mx = interior ? tile_row_max<false>(tmem_s + lane_off, rm, j0)
+                                : tile_row_max<true>(tmem_s + lane_off, rm, j0);
       const float m_new = fmaxf(m, mx * sc);
       const float m_use = m_new == -CUDART_INF_F ? 0.f : m_new;
       const float corr = ex2(m - m_use);
@@ -226,36 +275,15 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
         __syncwarp();
         if (lane == 0) mbar_arrive(o_empty);
       }
-      // rescale the accumulator for the new maximum
+      // rescale the accumulator only when the running maximum moved
+      if (corr != 1.f) {
 #pragma unroll
-      for (int i = 0; i < HD; ++i) acc[i] *= corr;
-      l *= corr;
-      m = m_new;
-      // pass 2: p = 2^(s*c - m) -> bf16 -> swizzled shared memory
-      float rs = 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_s + lane_off + c0, r);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = rm.ok(j0 + c0 + i) ? ex2(__uint_as_float(r[i]) * sc - m_use) : 0.f;
-          const float p1 = rm.ok(j0 + c0 + i + 1) ? ex2(__uint_as_float(r[i + 1]) * sc - m_use) : 0.f;
-          rs += p0 + p1;
-          __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t *>(&pp);
-        }
-        // 32 keys = 4 chunks of 16 B in k-block (c0 / 64), chunk index ((c0 % 64) / 8 + j)
-        uint8_t *blk = sP + (c0 >> 6) * kQBytes + row * 128;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int chunk = ((c0 & 63) >> 3) + j;
-          *reinterpret_cast<uint4 *>(blk + ((chunk ^ (row & 7)) << 4)) =
-              make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        }
+        for (int i = 0; i < HD; ++i) acc[i] *= corr;
+        l *= corr;
       }
-      l += rs;
+      m = m_new;
+      l += interior ? tile_row_p<false>(tmem_s + lane_off, rm, j0, sc, m_use, sP, row)
+                    : tile_row_p<true>(tmem_s + lane_off, rm, j0, sc, m_use, sP, row);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P visible to the tensor-core proxy
       tcgen05_fence_before();
       __syncwarp();
