@@ -19,7 +19,10 @@ eng.quiet = True
 if os.environ.get('VB_NO_GRAPH'):
     eng.use_cuda_graph = False
 texts, prompts = bench.make_batch(B, 0, dev)
-out = eng.generate(texts, prompts, top_k=1, max_new_tokens=None if frames >= bench.FRAMES else frames, return_device=True)
+mnt = None if frames >= bench.FRAMES else frames
+if os.environ.get('VB_WARM'):
+    eng.generate(texts, prompts, top_k=1, max_new_tokens=mnt, return_device=True)
+out = eng.generate(texts, prompts, top_k=1, max_new_tokens=mnt, return_device=True)
 torch.cuda.synchronize()
 print("frames", out[0].shape, "ar_ms", eng.stats.ar_ms, "steps", eng.stats.ar_steps, "nar_ms", eng.stats.nar_ms,
       "prefill_ms", eng.stats.prefill_ms)

@@ -379,7 +379,7 @@ attn_decode_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *_
 }
 
 // two-phase variant (scores of the whole chunk to shared memory, block softmax, then P.V)
-template <typename T>
+template <typename T, int U>
 __global__ void __launch_bounds__(128)
 attn_decode_2phase_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *__restrict__ kcache,
                    T *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
@@ -437,20 +437,17 @@ attn_decode_2phase_kernel(const float *__restrict__ q, QkvPartials qp, int n_hea
 #pragma unroll
   for (int i = 0; i < 8; ++i) qf[i] = qs[j8 + i];
   float lmax = -CUDART_INF_F;
-  for (int base = 0; base < n; base += 64) {
-    float kf[4][8];
+  const bool new_here = has_new && pos >= c0 && pos < c1;  // the current token's key lives in smem
+  for (int base = 0; base < n; base += 16 * U) {
+    float kf[U][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int key = base + u * 16 + warp * 4 + g;
       const int kk = min(key, n - 1);
       KvRow8<T>::load(kb + (int64_t)(c0 + kk) * HD + j8, kf[u]);
-      if (has_new && c0 + kk == pos) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) kf[u][i] = knew[j8 + i];
-      }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int key = base + u * 16 + warp * 4 + g;
       float dot = 0.f;
 #pragma unroll
@@ -458,10 +455,24 @@ attn_decode_2phase_kernel(const float *__restrict__ q, QkvPartials qp, int n_hea
       dot += __shfl_xor_sync(0xffffffffu, dot, 4);
       dot += __shfl_xor_sync(0xffffffffu, dot, 2);
       dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-      if ((lane & 7) == 0 && key < n) {
+      if ((lane & 7) == 0 && key < n && !(new_here && c0 + key == pos)) {
         sc[key] = dot;
         lmax = fmaxf(lmax, dot);
       }
+    }
+  }
+  if (new_here && warp == 0) {  // score of the current token from the shared-memory key (never from the cache)
+    float dot = 0.f;
+    if (lane < 8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], knew[j8 + i], dot);
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    if (lane == 0) {
+      sc[pos - c0] = dot;
+      lmax = fmaxf(lmax, dot);
     }
   }
   lmax = warp_max(lmax);
@@ -484,24 +495,25 @@ attn_decode_2phase_kernel(const float *__restrict__ q, QkvPartials qp, int n_hea
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int base = 0; base < n; base += 64) {
-    float vf[4][8];
-    float pv[4];
+  for (int base = 0; base < n; base += 16 * U) {
+    float vf[U][8];
+    float pv[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int key = base + u * 16 + jl;
       const int kk = min(key, n - 1);
-      pv[u] = key < n ? sc[kk] : 0.f;
+      pv[u] = (key < n && !(new_here && c0 + key == pos)) ? sc[kk] : 0.f;
       KvRow8<T>::load(vb_ + (int64_t)(c0 + kk) * HD + eg, vf[u]);
-      if (has_new && c0 + kk == pos) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) vf[u][i] = vnew[eg + i];
-      }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < U; ++u)
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = fmaf(pv[u], vf[u][i], acc[i]);
+  }
+  if (new_here && jl == 0) {
+    const float pn = sc[pos - c0];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pn, vnew[eg + i], acc[i]);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[jl][eg + i] = acc[i];
@@ -579,8 +591,12 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
     VB_CUDA(launch_kernel(attn_decode_kernel<float>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (float *)kcache,
                           (float *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
                           (bf16 *)out16, part_o, part_ml, ns));
+  else if (getenv("VB_ATTN_DECODE_1PASS") == nullptr && getenv("VB_ATTN_DECODE_U4") != nullptr)
+    VB_CUDA(launch_kernel(attn_decode_2phase_kernel<bf16, 4>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
+                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
+                          (bf16 *)out16, part_o, part_ml, ns));
   else if (getenv("VB_ATTN_DECODE_1PASS") == nullptr)
-    VB_CUDA(launch_kernel(attn_decode_2phase_kernel<bf16>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
+    VB_CUDA(launch_kernel(attn_decode_2phase_kernel<bf16, 8>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
                           (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
                           (bf16 *)out16, part_o, part_ml, ns));
   else

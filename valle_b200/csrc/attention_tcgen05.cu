@@ -10,9 +10,11 @@
 //                          O_t = P V   (M=128, N=64, K=16 x8, TMEM columns 128..191; P from shared
 //                          memory as the K-major A operand, V as an MN-major B operand -- the V tile
 //                          is used exactly as TMA lands it, no transpose)
-//   warps 2-5 softmax: ONE THREAD OWNS ONE QUERY ROW (TMEM lane): row max / sum without shuffles,
+//   warps 2-9 softmax: TWO THREADS OWN ONE QUERY ROW (TMEM lane): warps 2-5 take score columns 0..63 and
+//             output dims 0..31, warps 6-9 columns 64..127 and dims 32..63; the row maximum is the only
+//             thing the pair exchanges (shared memory + a 64-thread named barrier).
 //             p = exp2(s*c - m) -> bf16 -> swizzled shared memory (A operand of P V); after the P V MMA
-//             the thread folds O_t into its fp32 accumulator row with the online-softmax correction.
+//             each thread folds its half of O_t into its fp32 accumulator with the online-softmax correction.
 // QK^T of tile j+1 is issued right after P V of tile j, so the tensor pipe works while the softmax
 // threads fold O_t; two CTAs fit per SM (112 KB smem, 256 TMEM columns each) and interleave.
 #include <math_constants.h>
@@ -27,13 +29,14 @@ namespace fa5 {
 using namespace tc;
 
 constexpr int HD = 64, BQ = 128, BKV = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;  // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
 constexpr int kQBytes = BQ * HD * 2;         // 16 KB
 constexpr int kKBytes = BKV * HD * 2;        // 16 KB
 constexpr int kStageBytes = 2 * kKBytes;     // K + V
 constexpr int kStages = 2;
 constexpr int kPBytes = BQ * BKV * 2;        // 32 KB (two 64-key K-blocks of [128 x 64])
-constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kPBytes + 256;  // 2 CTAs per SM must fit
+constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kPBytes + 96 + 512;  // barriers + xch
+static_assert(2 * (kSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM must fit");
 constexpr int kTmemCols = 256;               // S: 128 cols, O_t: 64 cols
 
 __device__ __forceinline__ float ex2(float x) {
@@ -55,18 +58,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
 // instruction descriptor with B MN-major (bit 16)
 __host__ __device__ constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }
 
-// row maximum of the raw scores of one 128-key tile (thread = TMEM lane)
+// row maximum of this thread's 64 raw scores (thread = TMEM lane, column half `hf`)
 template <bool kMask>
-__device__ __forceinline__ float tile_row_max(uint32_t taddr, const RowMask &rm, int j0) {
+__device__ __forceinline__ float half_row_max(uint32_t taddr, const RowMask &rm, int jc0) {
   float mx = -CUDART_INF_F;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BKV; c0 += 32) {
+  for (int c0 = 0; c0 < 64; c0 += 32) {
     uint32_t r[32];
     tmem_ld32(taddr + c0, r);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       if (kMask) {
-        if (rm.ok(j0 + c0 + i)) mx = fmaxf(mx, __uint_as_float(r[i]));
+        if (rm.ok(jc0 + c0 + i)) mx = fmaxf(mx, __uint_as_float(r[i]));
       } else {
         mx = fmaxf(mx, __uint_as_float(r[i]));
       }
@@ -74,14 +77,14 @@ __device__ __forceinline__ float tile_row_max(uint32_t taddr, const RowMask &rm,
   }
   return mx;
 }
-// p = 2^(s*c - m) -> bf16 -> swizzled shared memory (K-major A operand of P V); returns the row sum
+// p = 2^(s*c - m) for 64 columns -> bf16 -> one 64-key k-block of the swizzled P tile; returns the sum
 template <bool kMask>
-__device__ __forceinline__ float tile_row_p(uint32_t taddr, const RowMask &rm, int j0, float sc, float m_use,
-                                            uint8_t *sP, int row) {
+__device__ __forceinline__ float half_row_p(uint32_t taddr, const RowMask &rm, int jc0, float sc, float m_use,
+                                            uint8_t *blk_row, int row) {
   float rs = 0.f;
   const float nm = -m_use;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BKV; c0 += 32) {
+  for (int c0 = 0; c0 < 64; c0 += 32) {
     uint32_t r[32];
     tmem_ld32(taddr + c0, r);
     uint32_t pk[16];
@@ -90,19 +93,17 @@ __device__ __forceinline__ float tile_row_p(uint32_t taddr, const RowMask &rm, i
       float p0 = ex2(fmaf(__uint_as_float(r[i]), sc, nm));
       float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), sc, nm));
       if (kMask) {
-        if (!rm.ok(j0 + c0 + i)) p0 = 0.f;
-        if (!rm.ok(j0 + c0 + i + 1)) p1 = 0.f;
+        if (!rm.ok(jc0 + c0 + i)) p0 = 0.f;
+        if (!rm.ok(jc0 + c0 + i + 1)) p1 = 0.f;
       }
       rs += p0 + p1;
       __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
       pk[i >> 1] = *reinterpret_cast<uint32_t *>(&pp);
     }
-    // 32 keys = 4 chunks of 16 B in k-block (c0 / 64), chunk index ((c0 % 64) / 8 + j)
-    uint8_t *blk = sP + (c0 >> 6) * kQBytes + row * 128;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int chunk = ((c0 & 63) >> 3) + j;
-      *reinterpret_cast<uint4 *>(blk + ((chunk ^ (row & 7)) << 4)) =
+      const int chunk = (c0 >> 3) + j;
+      *reinterpret_cast<uint4 *>(blk_row + ((chunk ^ (row & 7)) << 4)) =
           make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
     }
   }
@@ -127,6 +128,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
   uint64_t *o_full = p_full + 1;           // O_t ready in TMEM
   uint64_t *o_empty = o_full + 1;          // O_t consumed, P buffer free (4 warp arrivals)
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 1);
+  float *xch = reinterpret_cast<float *>(tmem_slot + 2);  // [128 rows] pair exchange slot
 
   const int b = blockIdx.z, h = blockIdx.y;
   const int r0 = cu_seqlens[b], L = cu_seqlens[b + 1] - r0;
@@ -148,9 +150,9 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
       mbar_init(&kv_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);   // one arrival per softmax warp
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
+    mbar_init(o_empty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -237,73 +239,93 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
     }
     __syncwarp();
   } else {
-    // ===== softmax: thread = one query row =====
+    // ===== softmax: two threads per query row =====
     const int quarter = warp & 3;                  // TMEM lanes this warp may touch
+    const int hf = (warp - 2) >> 2;                // 0: score cols 0..63 / dims 0..31, 1: cols 64..127 / dims 32..63
     const int row = quarter * 32 + lane;           // row within the tile
     const int qr = q0 + row;
     const RowMask rm = make_row_mask(mask_mode, qr, L, S, seg1_start, c1);
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t s_addr = tmem_s + lane_off + hf * 64;
+    const uint32_t o_addr = tmem_o + lane_off + hf * 32;
+    uint8_t *p_row = sP + hf * kQBytes + row * 128;
     const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    float acc[HD];
+    float acc[32];
 #pragma unroll
-    for (int i = 0; i < HD; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
     float m = -CUDART_INF_F, l = 0.f;
     for (int t = 0; t < n_tiles; ++t) {
-      const int j0 = t * BKV;
+      const int j0 = t * BKV, jc0 = j0 + hf * 64;
       mbar_wait(s_full, t & 1);
       tcgen05_fence_after();
-      // interior tile: every key of the tile is visible to this row -> no per-element mask
+      // interior tile: every key of the tile is visible to the rows of this warp -> no per-element mask
       // (warp-uniform: tcgen05.ld is .sync.aligned, a diverged warp must never reach it)
       const bool interior = __all_sync(0xffffffffu, j0 + BKV <= rm.lim0);
-      const float mx = interior ? tile_row_max<false>(tmem_s + lane_off, rm, j0)
-                                : tile_row_max<true>(tmem_s + lane_off, rm, j0);
+      float mx = interior ? half_row_max<false>(s_addr, rm, jc0) : half_row_max<true>(s_addr, rm, jc0);
+      // exchange the half-row maxima with the partner thread (same row, other column half)
+      if (hf == 1) xch[row] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      if (hf == 0) {
+        mx = fmaxf(mx, xch[row]);
+        xch[row] = mx;
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      if (hf == 1) mx = xch[row];
       const float m_new = fmaxf(m, mx * sc);
       const float m_use = m_new == -CUDART_INF_F ? 0.f : m_new;
       const float corr = ex2(m - m_use);
-      // previous P V must have consumed the P buffer before it is overwritten
+      // fold O_t of the previous tile (this also guarantees the previous P V has consumed the P buffer)
       if (t > 0) {
         mbar_wait(o_full, (t - 1) & 1);
         tcgen05_fence_after();
+        uint32_t r[32];
+        tmem_ld32(o_addr, r);
 #pragma unroll
-        for (int c0 = 0; c0 < HD; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_o + lane_off + c0, r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[c0 + i] += __uint_as_float(r[i]);
-        }
+        for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_empty);
       }
-      // rescale the accumulator only when the running maximum moved
-      if (corr != 1.f) {
+      if (corr != 1.f) {  // rescale only when the running maximum moved
 #pragma unroll
-        for (int i = 0; i < HD; ++i) acc[i] *= corr;
+        for (int i = 0; i < 32; ++i) acc[i] *= corr;
         l *= corr;
       }
       m = m_new;
-      l += interior ? tile_row_p<false>(tmem_s + lane_off, rm, j0, sc, m_use, sP, row)
-                    : tile_row_p<true>(tmem_s + lane_off, rm, j0, sc, m_use, sP, row);
+      l += interior ? half_row_p<false>(s_addr, rm, jc0, sc, m_use, p_row, row)
+                    : half_row_p<true>(s_addr, rm, jc0, sc, m_use, p_row, row);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P visible to the tensor-core proxy
       tcgen05_fence_before();
+      // the partner must have read this thread's xch slot before the next tile overwrites it: the
+      // named barrier of the next iteration orders that (write -> bar -> read -> ... -> next write
+      // happens after the partner passed this iteration's read because both arrive at p_full first)
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
     // last O_t
     mbar_wait(o_full, (n_tiles - 1) & 1);
     tcgen05_fence_after();
-#pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 32) {
+    {
       uint32_t r[32];
-      tmem_ld32(tmem_o + lane_off + c0, r);
+      tmem_ld32(o_addr, r);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+      for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
     }
+    // row sum = both halves
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // partner done with the max slot
+    if (hf == 1) xch[row] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+    if (hf == 0) {
+      l += xch[row];
+      xch[row] = l;
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+    if (hf == 1) l = xch[row];
     if (qr < L) {
       const float inv = 1.f / l;
-      uint4 *dst = reinterpret_cast<uint4 *>(out + (int64_t)(r0 + qr) * d + h * HD);
+      uint4 *dst = reinterpret_cast<uint4 *>(out + (int64_t)(r0 + qr) * d + h * HD + hf * 32);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         __nv_bfloat162 a0 = __floats2bfloat162_rn(acc[8 * j] * inv, acc[8 * j + 1] * inv);
         __nv_bfloat162 a1 = __floats2bfloat162_rn(acc[8 * j + 2] * inv, acc[8 * j + 3] * inv);
         __nv_bfloat162 a2 = __floats2bfloat162_rn(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv);
