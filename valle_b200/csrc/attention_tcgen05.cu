@@ -206,11 +206,28 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
         tcgen05_commit(s_full);
       }
       for (int t = 0; t < n_tiles; ++t) {
-        // ---- O_t = P(t) V(t) ----
         mbar_wait(p_full, t & 1);                 // P(t) written, S(t) consumed
-        if (t > 0) mbar_wait(o_empty, (t - 1) & 1);  // O_t(t-1) folded
         tcgen05_fence_after();
-        const uint32_t v_addr = smem_u32(sKV + stage * kStageBytes + kKBytes);
+        const int vstage = stage;
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+        // ---- S(t+1) = Q K(t+1)^T first: the softmax threads wait on it, P V runs behind it ----
+        if (t + 1 < n_tiles) {
+          mbar_wait(&kv_full[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t kdesc = make_smem_desc(smem_u32(sKV + stage * kStageBytes));
+#pragma unroll
+          for (int k = 0; k < HD / UMMA_K; ++k) umma_bf16(tmem_s, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
+          tcgen05_commit(s_full);
+        }
+        // ---- O_t = P(t) V(t) ----
+        if (t > 0) {
+          mbar_wait(o_empty, (t - 1) & 1);        // O_t(t-1) folded
+          tcgen05_fence_after();
+        }
+        const uint32_t v_addr = smem_u32(sKV + vstage * kStageBytes + kKBytes);
         const uint64_t vdesc = make_smem_desc_mn(v_addr);
 #pragma unroll
         for (int k = 0; k < BKV / UMMA_K; ++k) {
@@ -221,20 +238,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
           umma_bf16(tmem_o, pd, vd, idesc_o, k != 0);
         }
         tcgen05_commit(o_full);
-        tcgen05_commit(&kv_empty[stage]);  // K(t), V(t) free once these MMAs retire
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-        // ---- S(t+1) = Q K(t+1)^T, overlapping the softmax threads' fold of O_t(t) ----
-        if (t + 1 < n_tiles) {
-          mbar_wait(&kv_full[stage], phase);
-          tcgen05_fence_after();
-          const uint64_t kdesc = make_smem_desc(smem_u32(sKV + stage * kStageBytes));
-#pragma unroll
-          for (int k = 0; k < HD / UMMA_K; ++k) umma_bf16(tmem_s, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
-          tcgen05_commit(s_full);
-        }
+        tcgen05_commit(&kv_empty[vstage]);  // K(t), V(t) free once these MMAs retire
       }
     }
     __syncwarp();
@@ -256,7 +260,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
     float m = -CUDART_INF_F, l = 0.f;
     for (int t = 0; t < n_tiles; ++t) {
       const int j0 = t * BKV, jc0 = j0 + hf * 64;
-      mbar_wait(s_full, t & 1);
+      if (lane == 0) mbar_wait(s_full, t & 1);   // one lane polls, the warp parks at the sync
+      __syncwarp();
       tcgen05_fence_after();
       // interior tile: every key of the tile is visible to the rows of this warp -> no per-element mask
       // (warp-uniform: tcgen05.ld is .sync.aligned, a diverged warp must never reach it)
@@ -276,7 +281,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
       const float corr = ex2(m - m_use);
       // fold O_t of the previous tile (this also guarantees the previous P V has consumed the P buffer)
       if (t > 0) {
-        mbar_wait(o_full, (t - 1) & 1);
+        if (lane == 0) mbar_wait(o_full, (t - 1) & 1);
+        __syncwarp();
         tcgen05_fence_after();
         uint32_t r[32];
         tmem_ld32(o_addr, r);
@@ -303,7 +309,8 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
       if (lane == 0) mbar_arrive(p_full);
     }
     // last O_t
-    mbar_wait(o_full, (n_tiles - 1) & 1);
+    if (lane == 0) mbar_wait(o_full, (n_tiles - 1) & 1);
+    __syncwarp();
     tcgen05_fence_after();
     {
       uint32_t r[32];
