@@ -71,14 +71,15 @@ attn_varlen_mma_kernel(const bf16 *__restrict__ qkv, int n_head, const int32_t *
                        const int32_t *__restrict__ text_lens, const int32_t *__restrict__ seg1_lens,
                        int seg1_start, int mask_mode, bf16 *__restrict__ out,
                        bf16 *__restrict__ kcache, bf16 *__restrict__ vcache, int64_t cache_seq_stride,
-                       int cache_cap) {
+                       int cache_cap, int tail_of_128) {
   __shared__ __align__(128) uint8_t sQ[BQ * 128];
   __shared__ __align__(128) uint8_t sK[2][BKV * 128];
   __shared__ __align__(128) uint8_t sV[2][BKV * 128];
 
   const int b = blockIdx.z, h = blockIdx.y;
   const int r0 = cu_seqlens[b], L = cu_seqlens[b + 1] - r0;
-  const int q0 = blockIdx.x * BQ;
+  // tail_of_128: only the rows past the last full 128-row tile (the tcgen05 kernel covers the rest)
+  const int q0 = (tail_of_128 ? (L & ~127) : 0) + blockIdx.x * BQ;
   if (q0 >= L) return;
   const int S = (mask_mode != VB_MASK_FULL) ? text_lens[b] : 0;
   const int c1 = (mask_mode >= VB_MASK_PADDED_AR) ? seg1_lens[b] : 0;
@@ -243,11 +244,11 @@ attn_varlen_mma_kernel(const bf16 *__restrict__ qkv, int n_head, const int32_t *
 int launch_attention_mma(const bf16 *qkv, int64_t M, int B, int n_head, const int32_t *cu_seqlens,
                          const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
                          int mask_mode, bf16 *out, bf16 *kcache,
-                         bf16 *vcache, int64_t cache_seq_stride, int cache_cap, cudaStream_t s) {
+                         bf16 *vcache, int64_t cache_seq_stride, int cache_cap, int tail_of_128, cudaStream_t s) {
   if (M == 0 || B == 0) return VB_OK;
-  dim3 grid((max_seqlen + fa::BQ - 1) / fa::BQ, n_head, B);
+  dim3 grid(tail_of_128 ? 2 : (max_seqlen + fa::BQ - 1) / fa::BQ, n_head, B);
   fa::attn_varlen_mma_kernel<<<grid, fa::kThreads, 0, s>>>(qkv, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, out,
-                                                          kcache, vcache, cache_seq_stride, cache_cap);
+                                                          kcache, vcache, cache_seq_stride, cache_cap, tail_of_128);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }

@@ -59,19 +59,43 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }
 
 // row maximum of this thread's 64 raw scores (thread = TMEM lane, column half `hf`)
+// chunk-local visibility of 32 consecutive keys starting at key index cb:
+// valid(i) = i < a  or  b0 <= i < b1   (the two segments of RowMask clamped to the chunk)
+struct ChunkMask {
+  int a, b0, b1;
+  __device__ __forceinline__ ChunkMask(const RowMask &rm, int cb) {
+    a = min(max(rm.lim0 - cb, 0), 32);
+    b0 = min(max(rm.s1 - cb, 0), 32);
+    b1 = min(max(rm.hi1 - cb, 0), 32);
+  }
+  __device__ __forceinline__ bool any() const { return a > 0 || b1 > b0; }
+  __device__ __forceinline__ bool has_seg1() const { return b1 > b0; }
+  __device__ __forceinline__ bool ok(int i) const { return i < a || (i >= b0 && i < b1); }
+};
+
+// row maximum of this thread's 64 raw scores (thread = TMEM lane, column half `hf`)
 template <bool kMask>
 __device__ __forceinline__ float half_row_max(uint32_t taddr, const RowMask &rm, int jc0) {
   float mx = -CUDART_INF_F;
 #pragma unroll 1
   for (int c0 = 0; c0 < 64; c0 += 32) {
     uint32_t r[32];
-    tmem_ld32(taddr + c0, r);
+    if (!kMask) {
+      tmem_ld32(taddr + c0, r);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      if (kMask) {
-        if (rm.ok(jc0 + c0 + i)) mx = fmaxf(mx, __uint_as_float(r[i]));
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+    } else {
+      const ChunkMask cm(rm, jc0 + c0);
+      if (!__any_sync(0xffffffffu, cm.any())) continue;   // nobody in the warp sees these 32 keys
+      tmem_ld32(taddr + c0, r);
+      if (!__any_sync(0xffffffffu, cm.has_seg1())) {       // common case: one prefix [0, a)
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (i < cm.a) mx = fmaxf(mx, __uint_as_float(r[i]));
       } else {
-        mx = fmaxf(mx, __uint_as_float(r[i]));
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (cm.ok(i)) mx = fmaxf(mx, __uint_as_float(r[i]));
       }
     }
   }
@@ -86,19 +110,38 @@ __device__ __forceinline__ float half_row_p(uint32_t taddr, const RowMask &rm, i
 #pragma unroll 1
   for (int c0 = 0; c0 < 64; c0 += 32) {
     uint32_t r[32];
-    tmem_ld32(taddr + c0, r);
     uint32_t pk[16];
+    bool live = true;
+    if (kMask) {
+      const ChunkMask cm(rm, jc0 + c0);
+      live = __any_sync(0xffffffffu, cm.any());
+      if (live) {
+        tmem_ld32(taddr + c0, r);
+        if (!__any_sync(0xffffffffu, cm.has_seg1())) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float p0 = ex2(fmaf(__uint_as_float(r[i]), sc, nm));
-      float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), sc, nm));
-      if (kMask) {
-        if (!rm.ok(jc0 + c0 + i)) p0 = 0.f;
-        if (!rm.ok(jc0 + c0 + i + 1)) p1 = 0.f;
+          for (int i = 0; i < 32; ++i)
+            if (i >= cm.a) r[i] = 0xff800000u;  // -inf -> p = 0
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (!cm.ok(i)) r[i] = 0xff800000u;
+        }
       }
-      rs += p0 + p1;
-      __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
-      pk[i >> 1] = *reinterpret_cast<uint32_t *>(&pp);
+    } else {
+      tmem_ld32(taddr + c0, r);
+    }
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ex2(fmaf(__uint_as_float(r[i]), sc, nm));
+        const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), sc, nm));
+        rs += p0 + p1;
+        __nv_bfloat162 pp = __floats2bfloat162_rn(p0, p1);
+        pk[i >> 1] = *reinterpret_cast<uint32_t *>(&pp);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = 0u;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -113,7 +156,7 @@ __device__ __forceinline__ float half_row_p(uint32_t taddr, const RowMask &rm, i
 __global__ void __launch_bounds__(kThreads, 2)
 attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const int32_t *__restrict__ cu_seqlens,
                     const int32_t *__restrict__ text_lens, const int32_t *__restrict__ seg1_lens, int seg1_start,
-                    int mask_mode, bf16 *__restrict__ out) {
+                    int mask_mode, bf16 *__restrict__ out, int skip_partial) {
   extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t *sQ = smem;
@@ -133,7 +176,7 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
   const int b = blockIdx.z, h = blockIdx.y;
   const int r0 = cu_seqlens[b], L = cu_seqlens[b + 1] - r0;
   const int q0 = blockIdx.x * BQ;
-  if (q0 >= L) return;
+  if (q0 >= L || (skip_partial && q0 + BQ > L)) return;  // ragged tail rows go to the 64-row warp-level kernel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = n_head * HD;
   const int S = (mask_mode != VB_MASK_FULL) ? text_lens[b] : 0;
@@ -357,7 +400,7 @@ bool attention_tcgen05_enabled() { return getenv("VB_ATTN_MMA_SYNC") == nullptr;
 
 int launch_attention_tcgen05(const bf16 *qkv, int64_t M, int B, int n_head, const int32_t *cu_seqlens,
                              const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
-                             int mask_mode, bf16 *out, cudaStream_t s) {
+                             int mask_mode, bf16 *out, int skip_partial, cudaStream_t s) {
   if (M == 0 || B == 0) return VB_OK;
   const int d = n_head * fa5::HD;
   CUtensorMap tm;
@@ -369,7 +412,7 @@ int launch_attention_tcgen05(const bf16 *qkv, int64_t M, int B, int n_head, cons
   }
   dim3 grid((max_seqlen + fa5::BQ - 1) / fa5::BQ, n_head, B);
   fa5::attn_tcgen05_kernel<<<grid, fa5::kThreads, fa5::kSmemBytes, s>>>(tm, n_head, cu_seqlens, text_lens, seg1_lens,
-                                                                      seg1_start, mask_mode, out);
+                                                                      seg1_start, mask_mode, out, skip_partial);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }

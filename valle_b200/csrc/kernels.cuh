@@ -68,12 +68,12 @@ int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_
 int launch_attention_mma(const bf16 *qkv, int64_t M, int B, int n_head, const int32_t *cu_seqlens,
                          const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
                          int mask_mode, bf16 *out, bf16 *kcache,
-                         bf16 *vcache, int64_t cache_seq_stride, int cache_cap, cudaStream_t s);
+                         bf16 *vcache, int64_t cache_seq_stride, int cache_cap, int tail_of_128, cudaStream_t s);
 // attention_tcgen05.cu (bf16 flash attention on tcgen05/TMEM; no KV-cache fill)
 bool attention_tcgen05_enabled();
 int launch_attention_tcgen05(const bf16 *qkv, int64_t M, int B, int n_head, const int32_t *cu_seqlens,
                              const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
-                             int mask_mode, bf16 *out, cudaStream_t s);
+                             int mask_mode, bf16 *out, int skip_partial, cudaStream_t s);
 size_t attn_decode_workspace(int B, int n_head, int head_dim, int cache_cap);
 int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, int qkv_ldp, const float *qkv_bias,
                        int B, int n_head, int head_dim, void *kcache, void *vcache, int dtype,
