@@ -187,7 +187,7 @@ int tc_head(vb_decoder *dec, const vb_ar_head *head, float *x, vb_ar_state *st, 
   const int ldl = (head->n_vocab + 3) & ~3;
   const bool pdl = use_pdl();
   VB_TRY(launch_ln_reduce(x, d, B, d, pend.part, pend.splits, pend.ldp, pend.bias, D.final_norm_w, D.final_norm_b,
-                          1e-5f, w.xn16, pdl, s));
+                          1e-5f, w.xn16, nullptr, pdl, s));
   int sp = 1, ldp = 0;
   VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)head->predict_w, head->n_vocab, d, 0, nullptr, DG_F32,
                             st->logits, nullptr, ldl, nullptr, (float *)w.gemm_ws, w.gemm_ws_bytes, &sp, &ldp, pdl, s));
@@ -242,6 +242,8 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
     // bf16 tensor-core path: LayerNorm(+pending residual) -> swap-AB split-K tcgen05 projections whose
     // partial sums are consumed by the next kernel in the chain (7 launches per layer, PDL-chained)
     const bool pdl = use_pdl();
+    static const int pf_env = getenv("VB_KV_PREFETCH_PCT") ? atoi(getenv("VB_KV_PREFETCH_PCT")) : 0;
+    const int pf_pct = B >= 16 ? pf_env : 0;
     float *P = (float *)w.gemm_ws;
     Pending pend;
     for (int l = 0; l < D.n_layer; ++l) {
@@ -250,7 +252,7 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
       void *vc = (char *)st->vcache + (size_t)l * st->cache_layer_stride * ts;
       QkvScatter sc{d, hd, w.q, kc, vc, st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen};
       VB_TRY(launch_ln_reduce(x, d, B, d, pend.part, pend.splits, pend.ldp, pend.bias, L.norm1_w, L.norm1_b, 1e-5f,
-                              w.xn16, pdl, s));
+                              w.xn16, nullptr, pdl, s));
       int s1 = 1, ldp1 = 0;
       VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.in_proj_w, 3 * d, d, 0, L.in_proj_b, DG_QKV, nullptr,
                                 nullptr, d, &sc, P, w.gemm_ws_bytes, &s1, &ldp1, pdl, s));
@@ -260,12 +262,19 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
       int s2 = 1, ldp2 = 0;
       VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)L.out_proj_w, d, d, 0, L.out_proj_b, DG_RESIDUAL, x,
                                 nullptr, d, nullptr, P, w.gemm_ws_bytes, &s2, &ldp2, pdl, s));
+      // the two small kernels ahead of the FFN projections pull (part of) the next layer's K / V stream into L2
+      const int ln = (l + 1) % D.n_layer;
+      KvPrefetch pfk{pf_pct > 0 ? (char *)st->kcache + (size_t)ln * st->cache_layer_stride * ts : nullptr,
+                     (int64_t)st->cache_seq_stride * (int64_t)ts, B, D.n_head, st->cache_cap, (int)(hd * ts),
+                     st->text_len, st->prompt_len, st->n_gen, pf_pct};
+      KvPrefetch pfv = pfk;
+      pfv.base = pf_pct > 0 ? (char *)st->vcache + (size_t)ln * st->cache_layer_stride * ts : nullptr;
       VB_TRY(launch_ln_reduce(x, d, B, d, s2 > 1 ? P : nullptr, s2, ldp2, L.out_proj_b, L.norm2_w, L.norm2_b, 1e-5f,
-                              w.xn16, pdl, s));
+                              w.xn16, &pfk, pdl, s));
       int sf = 1, ldpf = 0;
       VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.lin1_w, dff, d, 0, L.lin1_b, DG_RELU_BF16, nullptr,
                                 w.hb16, dff, nullptr, P, w.gemm_ws_bytes, &sf, &ldpf, pdl, s));
-      if (sf > 1) VB_TRY(launch_relu_reduce(P, sf, ldpf, L.lin1_b, B, dff, w.hb16, dff, pdl, s));
+      if (sf > 1) VB_TRY(launch_relu_reduce(P, sf, ldpf, L.lin1_b, B, dff, w.hb16, dff, &pfv, pdl, s));
       int s3 = 1, ldp3 = 0;
       VB_TRY(launch_gemm_decode(w.hb16, B, dff, (const bf16 *)L.lin2_w, d, dff, 0, L.lin2_b, DG_RESIDUAL, x, nullptr,
                                 d, nullptr, P, w.gemm_ws_bytes, &s3, &ldp3, pdl, s));

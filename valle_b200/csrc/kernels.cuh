@@ -25,6 +25,32 @@ __device__ __forceinline__ RowMask make_row_mask(int mode, int qr, int L, int S,
   return m;
 }
 
+// L2 prefetch of (part of) the NEXT layer's K or V cache, issued by the small kernels of the decode chain
+// before their dependency wait: the chain is latency bound and leaves HBM idle, the attention kernel that
+// follows is HBM bound -- overlapping the two moves part of its stream into the 126 MB L2.
+struct KvPrefetch {
+  const void *base;          // cache of one layer ([B, H, cap, 64]) or nullptr
+  int64_t seq_stride_bytes;  // bytes between utterances
+  int B, H, cap, row_bytes;  // row_bytes = 64 * element size
+  const int32_t *text_len, *prompt_len, *n_gen;
+  int pct;                   // percentage of each (b, h) stream to prefetch
+};
+__device__ __forceinline__ void kv_prefetch(const KvPrefetch &pf) {
+  if (pf.base == nullptr) return;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int gw = (blockIdx.y * gridDim.x + blockIdx.x) * warps_per_cta + (threadIdx.x >> 5);
+  const int GW = gridDim.x * gridDim.y * warps_per_cta;
+  for (int pair = gw; pair < pf.B * pf.H; pair += GW) {
+    const int b = pair / pf.H, h = pair - b * pf.H;
+    int kv = pf.text_len[b] + pf.prompt_len[b] + pf.n_gen[b];
+    kv = min(kv, pf.cap) * pf.pct / 100;
+    const char *p = (const char *)pf.base + (int64_t)b * pf.seq_stride_bytes + (int64_t)h * pf.cap * pf.row_bytes;
+    const int lines = (kv * pf.row_bytes) >> 7;  // 128-byte lines
+    for (int i = lane; i < lines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + ((int64_t)i << 7)));
+  }
+}
+
 struct LnParams {
   const float *gamma, *beta, *ada_wb;  // ada_wb: NULL or [2d] (weight | bias)
   float eps;
@@ -88,10 +114,10 @@ int launch_attn_decode_tma(const float *q, const float *qkv_part, int qkv_splits
 
 // decode_fused.cu
 int launch_relu_reduce(const float *partials, int splits, int ldp, const float *bias, int B, int N, bf16 *out16,
-                       int64_t ldo, bool pdl, cudaStream_t s);
+                       int64_t ldo, const KvPrefetch *pf, bool pdl, cudaStream_t s);
 int launch_ln_reduce(float *x, int64_t ldx, int B, int d, const float *partials, int splits, int ldp,
-                     const float *bias, const float *gamma, const float *beta, float eps, bf16 *out16, bool pdl,
-                     cudaStream_t s);
+                     const float *bias, const float *gamma, const float *beta, float eps, bf16 *out16,
+                     const KvPrefetch *pf, bool pdl, cudaStream_t s);
 
 // sample.cu
 int launch_ar_sample(float *logits, int64_t ld_logits, const float *partials, int splits, int ldp,
