@@ -37,20 +37,22 @@ template <int BN> struct Cfg {
   static constexpr int kABytes = BM * BK * 2;  // 16 KB
   static constexpr int kBBytes = BN * BK * 2;  // 32 KB / 16 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 2 * BM * 128;  // two 128-row x 128-byte epilogue staging boxes
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;     // 512 / 256: power of two >= 32
 };
 
 template <int BN, int kEpi, typename TC>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const float *__restrict__ bias, TC *__restrict__ C, int64_t ldc, int M, int N, int K) {
+                    const __grid_constant__ CUtensorMap tmap_c, const float *__restrict__ bias, int M, int N, int K) {
   using cfg = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *tiles = smem;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + cfg::kStages * cfg::kStageBytes);
+  uint8_t *staging = smem + cfg::kStages * cfg::kStageBytes;  // [2][128 rows x 128 B], 128B-swizzled
+  uint64_t *bars = reinterpret_cast<uint64_t *>(staging + cfg::kStagingBytes);
   uint64_t *full_bar = bars;                       // [kStages]
   uint64_t *empty_bar = bars + cfg::kStages;       // [kStages]
   uint64_t *tmem_full = bars + 2 * cfg::kStages;   // [2]
@@ -146,57 +148,66 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ===== epilogue =====
+    // ===== epilogue: TMEM -> registers (+bias, ReLU) -> 128B-swizzled staging box -> TMA store =====
+    // fp32 residual outputs use cp.reduce.async.bulk (.add): the residual add of transformer.py:297-302
+    // happens in the memory system, x is never read by the SM.
+    constexpr int kColsPerUnit = 128 / (int)sizeof(TC);  // 32 fp32 or 64 bf16 columns = one 128-byte row
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_l = q * 32 + lane;
+    const bool issuer = (warp == 4 && lane == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
+    int unit = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_blk = t / n_tiles, n_blk = t % n_tiles;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = m_blk * BM + q * 32 + lane;
-      const bool row_ok = row < M;
-      TC *crow = C + (int64_t)(row_ok ? row : 0) * ldc + n_blk * BN;
       const float *brow = bias ? bias + n_blk * BN : nullptr;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0), r);
-        float v[32];
+      for (int c0 = 0; c0 < BN; c0 += kColsPerUnit, ++unit) {
+        uint8_t *box = staging + (unit & 1) * (BM * 128);
+        // the TMA store issued two units ago (same box) must have finished READING shared memory
+        if (issuer) tma_store_wait_read<1>();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        uint8_t *srow = box + row_l * 128;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = __uint_as_float(r[i]);
-          if (brow) v[i] += __ldg(brow + c0 + i);
-          if constexpr (kEpi == VB_EPI_RELU) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (row_ok) {
+        for (int h = 0; h < kColsPerUnit / 32; ++h) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c0 + h * 32), r);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] = __uint_as_float(r[i]);
+            if (brow) v[i] += __ldg(brow + c0 + h * 32 + i);
+            if constexpr (kEpi == VB_EPI_RELU) v[i] = fmaxf(v[i], 0.f);
+          }
           if constexpr (sizeof(TC) == 4) {
-            float4 *dst = reinterpret_cast<float4 *>(crow + c0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-              if constexpr (kEpi == VB_EPI_RESIDUAL) {
-                const float4 old = dst[i];
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              dst[i] = o;
-            }
+            for (int j = 0; j < 8; ++j)  // 8 chunks of 4 floats
+              *reinterpret_cast<float4 *>(srow + ((j ^ (row_l & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            uint4 *dst = reinterpret_cast<uint4 *>(crow + c0);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
-              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
-              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
-              uint4 o;
-              o.x = *reinterpret_cast<uint32_t *>(&p0);
-              o.y = *reinterpret_cast<uint32_t *>(&p1);
-              o.z = *reinterpret_cast<uint32_t *>(&p2);
-              o.w = *reinterpret_cast<uint32_t *>(&p3);
-              dst[i] = o;
+            for (int j = 0; j < 4; ++j) {  // 4 chunks of 8 bf16 (this half of the 64-column unit)
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+              const int chunk = h * 4 + j;
+              *reinterpret_cast<uint4 *>(srow + ((chunk ^ (row_l & 7)) << 4)) =
+                  make_uint4(*reinterpret_cast<uint32_t *>(&p0), *reinterpret_cast<uint32_t *>(&p1),
+                             *reinterpret_cast<uint32_t *>(&p2), *reinterpret_cast<uint32_t *>(&p3));
             }
           }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // staging visible to the TMA engine
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer) {
+          if constexpr (kEpi == VB_EPI_RESIDUAL)
+            tma_reduce_add_2d(&tmap_c, box, n_blk * BN + c0, m_blk * BM);
+          else
+            tma_store_2d(&tmap_c, box, n_blk * BN + c0, m_blk * BM);
+          tma_store_commit();
         }
       }
       tcgen05_fence_before();
@@ -207,6 +218,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         acc_phase ^= 1;
       }
     }
+    if (issuer) tma_store_wait_read<0>();  // shared memory must outlive the last store's reads
   }
   __syncwarp();
   tcgen05_fence_before();
@@ -220,6 +232,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 template <int BN, int kEpi, typename TC>
 static int launch_t(const CUtensorMap &ta, const CUtensorMap &tb, const float *bias, TC *C, int64_t ldc, int M,
                     int N, int K, cudaStream_t s) {
+  CUtensorMap tcm;
+  VB_TRY(tc::make_tmap_2d(&tcm, C, M, N, ldc, BM, 128 / (int)sizeof(TC), sizeof(TC) == 4));
   using cfg = Cfg<BN>;
   auto kern = gemm_tcgen05_kernel<BN, kEpi, TC>;
   static bool attr_set = false;  // per template instantiation
@@ -229,7 +243,7 @@ static int launch_t(const CUtensorMap &ta, const CUtensorMap &tb, const float *b
   }
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kThreads, cfg::kSmemBytes, s>>>(ta, tb, bias, C, ldc, M, N, K);
+  kern<<<grid, kThreads, cfg::kSmemBytes, s>>>(ta, tb, tcm, bias, M, N, K);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }

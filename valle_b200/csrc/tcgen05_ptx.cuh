@@ -121,6 +121,46 @@ inline EncodeTiledFn get_encode() {
   return fn;
 }
 
+// general 2-D row-major tensor map: [rows, cols] of `esize`-byte elements, leading dimension ld (elements),
+// box = [box_rows, box_cols] with box_cols * esize == 128 (one 128-byte swizzle span)
+inline int make_tmap_2d(CUtensorMap *map, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                        int box_cols, bool f32) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("tensor map: cuTensorMapEncodeTiled entry point unavailable");
+    return VB_ERR_CUDA;
+  }
+  const int es = f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tensor map: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, (long long)rows,
+              (long long)cols, (long long)ld);
+    return VB_ERR_CUDA;
+  }
+  return VB_OK;
+}
+// TMA stores from a 128B-swizzled shared-memory box (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // row-major [rows, K] bf16 matrix with leading dimension ld (elements); box = [box_rows, 64]
 inline int make_tmap(CUtensorMap *map, const void *ptr, int64_t rows, int K, int64_t ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
