@@ -19,6 +19,19 @@ eng.quiet = True
 if os.environ.get('VB_NO_GRAPH'):
     eng.use_cuda_graph = False
 texts, prompts = bench.make_batch(B, 0, dev)
+if len(sys.argv) > 4 and sys.argv[4] == 'nar':
+    # NAR only: VALLE.continual on [prompt | 753 given first-codebook frames] -> the 7 NAR passes of the bench shape
+    g = torch.Generator().manual_seed(1)
+    ys = [torch.randint(0, 1024, (bench.T_PROMPT + frames, bench.N_Q), generator=g).to(dev) for _ in range(B)]
+    eng.continual(texts, ys)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.continual(texts, ys)
+    e1.record()
+    torch.cuda.synchronize()
+    print('nar_only_ms', e0.elapsed_time(e1))
+    sys.exit(0)
 mnt = None if frames >= bench.FRAMES else frames
 if os.environ.get('VB_WARM'):
     eng.generate(texts, prompts, top_k=1, max_new_tokens=mnt, return_device=True)
