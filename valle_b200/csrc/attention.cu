@@ -186,12 +186,10 @@ int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_
     k<<<grid, 256, smem, s>>>((const float *)qkv, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, (float *)out,
                               (float *)kcache, (float *)vcache, cache_seq_stride, cache_cap);
   } else if (dtype == VB_BF16 && kcache == nullptr && getenv("VB_ATTN_SIMT") == nullptr && attention_tcgen05_enabled()) {
-    // full 128-row query tiles on tcgen05/TMEM; the ragged tail rows (< 128 per sequence) on the
-    // 64-row warp-level kernel, so a length like 1025 does not pay for a ninth 128-row tile
-    VB_TRY(launch_attention_tcgen05((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start,
-                                    max_seqlen, mask_mode, (bf16 *)out, 1, s));
-    return launch_attention_mma((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start,
-                                max_seqlen, mask_mode, (bf16 *)out, nullptr, nullptr, 0, 0, 1, s);
+    // 128-row query tiles on tcgen05/TMEM; a ragged last tile is shifted back to [L-128, L) (overlap, rows are
+    // independent) so that a length like 1025 costs 9 tiles, not 9 tiles plus a 64-row warp-level pass
+    return launch_attention_tcgen05((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start,
+                                    max_seqlen, mask_mode, (bf16 *)out, 2, s);
   } else if (dtype == VB_BF16 && getenv("VB_ATTN_SIMT") == nullptr) {
     return launch_attention_mma((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, max_seqlen, mask_mode,
                                 (bf16 *)out, (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, 0, s);

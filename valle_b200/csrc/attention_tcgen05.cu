@@ -175,8 +175,15 @@ attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const 
 
   const int b = blockIdx.z, h = blockIdx.y;
   const int r0 = cu_seqlens[b], L = cu_seqlens[b + 1] - r0;
-  const int q0 = blockIdx.x * BQ;
-  if (q0 >= L || (skip_partial && q0 + BQ > L)) return;  // ragged tail rows go to the 64-row warp-level kernel
+  // skip_partial == 1: ragged tail rows go to the 64-row warp-level kernel.
+  // skip_partial == 2: the last tile is shifted back to rows [L - 128, L): it overlaps its predecessor, the
+  //   overlapping rows are recomputed bit-identically (rows are independent) and stored twice.
+  int q0 = blockIdx.x * BQ;
+  if (q0 >= L) return;
+  if (q0 + BQ > L) {
+    if (skip_partial == 1) return;
+    if (skip_partial == 2 && L >= BQ) q0 = L - BQ;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = n_head * HD;
   const int S = (mask_mode != VB_MASK_FULL) ? text_lens[b] : 0;
