@@ -5,6 +5,8 @@
 
 #include <new>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -187,10 +189,11 @@ int tc_head(vb_decoder *dec, const vb_ar_head *head, float *x, vb_ar_state *st, 
   const int ldl = (head->n_vocab + 3) & ~3;
   const bool pdl = use_pdl();
   VB_TRY(launch_ln_reduce(x, d, B, d, pend.part, pend.splits, pend.ldp, pend.bias, D.final_norm_w, D.final_norm_b,
-                          1e-5f, w.xn16, nullptr, pdl, s));
+                          1e-5f, w.xn16, pdl, s));
   int sp = 1, ldp = 0;
   VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)head->predict_w, head->n_vocab, d, 0, nullptr, DG_F32,
-                            st->logits, nullptr, ldl, nullptr, (float *)w.gemm_ws, w.gemm_ws_bytes, &sp, &ldp, pdl, s));
+                            st->logits, nullptr, ldl, nullptr, (float *)w.gemm_ws, w.gemm_ws_bytes, &sp, &ldp, nullptr, pdl,
+                            s));
   if (head->greedy)
     VB_TRY(launch_ar_sample(st->logits, ldl, sp > 1 ? (const float *)w.gemm_ws : nullptr, sp, ldp, head, st, d, nullptr,
                             0, pdl, s));
@@ -242,42 +245,60 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
     // bf16 tensor-core path: LayerNorm(+pending residual) -> swap-AB split-K tcgen05 projections whose
     // partial sums are consumed by the next kernel in the chain (7 launches per layer, PDL-chained)
     const bool pdl = use_pdl();
-    static const int pf_env = getenv("VB_KV_PREFETCH_PCT") ? atoi(getenv("VB_KV_PREFETCH_PCT")) : 0;
+    // Tuning of the chain (measured on B200 at d=1024 / d_ff=4096 / B=64, profiles/round1_summary.md): split-K wide
+    // enough to fill the SMs is not the optimum for the projections whose partial sums a reduce kernel has to add
+    // up again (FFN2: 9 splits beat 18, QKV: 5 beat 6); 40 % of the KV streams prefetched into L2 beat 20 / 60 %.
+    static const int pf_env = getenv("VB_KV_PREFETCH_PCT") ? atoi(getenv("VB_KV_PREFETCH_PCT")) : 40;
     const int pf_pct = B >= 16 ? pf_env : 0;
+    static const int qkv_env = getenv("VB_SPLITS_QKV") ? atoi(getenv("VB_SPLITS_QKV")) : 0;
+    static const int out_splits = getenv("VB_SPLITS_OUT") ? atoi(getenv("VB_SPLITS_OUT")) : 0;   // 0 = fill the SMs
+    static const int ffn1_splits = getenv("VB_SPLITS_FFN1") ? atoi(getenv("VB_SPLITS_FFN1")) : 0;
+    static const int ffn2_env = getenv("VB_SPLITS_FFN2") ? atoi(getenv("VB_SPLITS_FFN2")) : 0;
+    const int qkv_splits = qkv_env > 0 ? qkv_env : std::max(1, std::min(5, d / 128));
+    const int ffn2_splits = ffn2_env > 0 ? ffn2_env : std::max(1, std::min(9, dff / 128));
     float *P = (float *)w.gemm_ws;
     Pending pend;
+    // the four projections of the chain each prefetch a quarter of the first pf_pct % of the KV streams that the
+    // NEXT attention launch will read (QKV: this layer's, the other three: the following layer's)
+    auto kv_slice = [&](int layer, int quarter) {
+      KvPrefetch pf{};
+      if (pf_pct <= 0) return pf;
+      layer %= D.n_layer;
+      pf.kbase = (char *)st->kcache + (size_t)layer * st->cache_layer_stride * ts;
+      pf.vbase = (char *)st->vcache + (size_t)layer * st->cache_layer_stride * ts;
+      pf.seq_stride_bytes = (int64_t)st->cache_seq_stride * (int64_t)ts;
+      pf.B = B; pf.H = D.n_head; pf.cap = st->cache_cap; pf.row_bytes = (int)(hd * ts);
+      pf.text_len = st->text_len; pf.prompt_len = st->prompt_len; pf.n_gen = st->n_gen;
+      pf.lo_pct = pf_pct * quarter / 4; pf.hi_pct = pf_pct * (quarter + 1) / 4;
+      return pf;
+    };
     for (int l = 0; l < D.n_layer; ++l) {
       const vb_layer_params &L = dec->layers[l];
+      const KvPrefetch pf_qkv = kv_slice(l, 3), pf_out = kv_slice(l + 1, 0), pf_f1 = kv_slice(l + 1, 1),
+                       pf_f2 = kv_slice(l + 1, 2);
       void *kc = (char *)st->kcache + (size_t)l * st->cache_layer_stride * ts;
       void *vc = (char *)st->vcache + (size_t)l * st->cache_layer_stride * ts;
       QkvScatter sc{d, hd, w.q, kc, vc, st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen};
       VB_TRY(launch_ln_reduce(x, d, B, d, pend.part, pend.splits, pend.ldp, pend.bias, L.norm1_w, L.norm1_b, 1e-5f,
-                              w.xn16, nullptr, pdl, s));
+                              w.xn16, pdl, s));
       int s1 = 1, ldp1 = 0;
-      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.in_proj_w, 3 * d, d, 0, L.in_proj_b, DG_QKV, nullptr,
-                                nullptr, d, &sc, P, w.gemm_ws_bytes, &s1, &ldp1, pdl, s));
+      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.in_proj_w, 3 * d, d, qkv_splits, L.in_proj_b, DG_QKV, nullptr,
+                                nullptr, d, &sc, P, w.gemm_ws_bytes, &s1, &ldp1, &pf_qkv, pdl, s));
       VB_TRY(launch_attn_decode(w.q, s1 > 1 ? P : nullptr, s1, ldp1, L.in_proj_b, B, D.n_head, hd, kc, vc, dt,
                                 st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen, w.att,
                                 w.att16, w.attn_ws, pdl, s));
       int s2 = 1, ldp2 = 0;
-      VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)L.out_proj_w, d, d, 0, L.out_proj_b, DG_RESIDUAL, x,
-                                nullptr, d, nullptr, P, w.gemm_ws_bytes, &s2, &ldp2, pdl, s));
-      // the two small kernels ahead of the FFN projections pull (part of) the next layer's K / V stream into L2
-      const int ln = (l + 1) % D.n_layer;
-      KvPrefetch pfk{pf_pct > 0 ? (char *)st->kcache + (size_t)ln * st->cache_layer_stride * ts : nullptr,
-                     (int64_t)st->cache_seq_stride * (int64_t)ts, B, D.n_head, st->cache_cap, (int)(hd * ts),
-                     st->text_len, st->prompt_len, st->n_gen, pf_pct};
-      KvPrefetch pfv = pfk;
-      pfv.base = pf_pct > 0 ? (char *)st->vcache + (size_t)ln * st->cache_layer_stride * ts : nullptr;
+      VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)L.out_proj_w, d, d, out_splits, L.out_proj_b, DG_RESIDUAL, x,
+                                nullptr, d, nullptr, P, w.gemm_ws_bytes, &s2, &ldp2, &pf_out, pdl, s));
       VB_TRY(launch_ln_reduce(x, d, B, d, s2 > 1 ? P : nullptr, s2, ldp2, L.out_proj_b, L.norm2_w, L.norm2_b, 1e-5f,
-                              w.xn16, &pfk, pdl, s));
+                              w.xn16, pdl, s));
       int sf = 1, ldpf = 0;
-      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.lin1_w, dff, d, 0, L.lin1_b, DG_RELU_BF16, nullptr,
-                                w.hb16, dff, nullptr, P, w.gemm_ws_bytes, &sf, &ldpf, pdl, s));
-      if (sf > 1) VB_TRY(launch_relu_reduce(P, sf, ldpf, L.lin1_b, B, dff, w.hb16, dff, &pfv, pdl, s));
+      VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.lin1_w, dff, d, ffn1_splits, L.lin1_b, DG_RELU_BF16, nullptr,
+                                w.hb16, dff, nullptr, P, w.gemm_ws_bytes, &sf, &ldpf, &pf_f1, pdl, s));
+      if (sf > 1) VB_TRY(launch_relu_reduce(P, sf, ldpf, L.lin1_b, B, dff, w.hb16, dff, pdl, s));
       int s3 = 1, ldp3 = 0;
-      VB_TRY(launch_gemm_decode(w.hb16, B, dff, (const bf16 *)L.lin2_w, d, dff, 0, L.lin2_b, DG_RESIDUAL, x, nullptr,
-                                d, nullptr, P, w.gemm_ws_bytes, &s3, &ldp3, pdl, s));
+      VB_TRY(launch_gemm_decode(w.hb16, B, dff, (const bf16 *)L.lin2_w, d, dff, ffn2_splits, L.lin2_b, DG_RESIDUAL, x, nullptr,
+                                d, nullptr, P, w.gemm_ws_bytes, &s3, &ldp3, &pf_f2, pdl, s));
       pend = Pending{};
       if (s3 > 1) {
         pend.part = P; pend.bias = L.lin2_b; pend.splits = s3; pend.ldp = ldp3;

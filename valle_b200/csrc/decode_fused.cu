@@ -14,10 +14,9 @@ template <int kSlabs>
 __global__ void __launch_bounds__(256)
 ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *__restrict__ partials, int splits,
                  int ldp, const float *__restrict__ bias, const float *__restrict__ gamma,
-                 const float *__restrict__ beta, float eps, bf16 *__restrict__ out16, KvPrefetch pf) {
+                 const float *__restrict__ beta, float eps, bf16 *__restrict__ out16) {
   __shared__ float red[2][8];
   pdl_launch_dependents();
-  kv_prefetch(pf);
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_wait();
   float *xr = x + (int64_t)b * ldx;
@@ -91,9 +90,8 @@ ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *
 // (valle/modules/transformer.py:332-334: linear1 -> ReLU), input rows of the linear2 projection.
 __global__ void __launch_bounds__(256)
 relu_reduce_kernel(const float *__restrict__ partials, int splits, int ldp, const float *__restrict__ bias, int N,
-                   bf16 *__restrict__ out16, int64_t ldo, KvPrefetch pf) {
+                   bf16 *__restrict__ out16, int64_t ldo) {
   pdl_launch_dependents();
-  kv_prefetch(pf);
   const int b = blockIdx.y;
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   pdl_wait();
@@ -115,33 +113,29 @@ relu_reduce_kernel(const float *__restrict__ partials, int splits, int ldp, cons
 }
 
 int launch_relu_reduce(const float *partials, int splits, int ldp, const float *bias, int B, int N, bf16 *out16,
-                       int64_t ldo, const KvPrefetch *pf, bool pdl, cudaStream_t s) {
-  KvPrefetch p0{};
-  if (pf) p0 = *pf;
+                       int64_t ldo, bool pdl, cudaStream_t s) {
   VB_CHECK_ARG(N % 4 == 0 && ldo % 4 == 0, "relu_reduce: N %% 4 != 0");
   VB_CUDA(launch_kernel(relu_reduce_kernel, dim3((N / 4 + 255) / 256, B), dim3(256), 0, s, pdl, partials, splits, ldp,
-                        bias, N, out16, ldo, p0));
+                        bias, N, out16, ldo));
   count_launch();
   return VB_OK;
 }
 
 int launch_ln_reduce(float *x, int64_t ldx, int B, int d, const float *partials, int splits, int ldp,
                      const float *bias, const float *gamma, const float *beta, float eps, bf16 *out16,
-                     const KvPrefetch *pf, bool pdl, cudaStream_t s) {
-  KvPrefetch p0{};
-  if (pf) p0 = *pf;
+                     bool pdl, cudaStream_t s) {
   VB_CHECK_ARG(d % 4 == 0 && ldx % 4 == 0 && d <= 4096, "ln_reduce: bad d=%d", d);
   const dim3 grid(B), block(256);
   const int slabs = (d + 1023) / 1024;
   if (slabs <= 1)
     VB_CUDA(launch_kernel(ln_reduce_kernel<1>, grid, block, 0, s, pdl, x, ldx, B, d, partials, splits, ldp, bias,
-                          gamma, beta, eps, out16, p0));
+                          gamma, beta, eps, out16));
   else if (slabs <= 2)
     VB_CUDA(launch_kernel(ln_reduce_kernel<2>, grid, block, 0, s, pdl, x, ldx, B, d, partials, splits, ldp, bias,
-                          gamma, beta, eps, out16, p0));
+                          gamma, beta, eps, out16));
   else
     VB_CUDA(launch_kernel(ln_reduce_kernel<4>, grid, block, 0, s, pdl, x, ldx, B, d, partials, splits, ldp, bias,
-                          gamma, beta, eps, out16, p0));
+                          gamma, beta, eps, out16));
   count_launch();
   return VB_OK;
 }

@@ -74,7 +74,7 @@ __device__ __forceinline__ void apply_epi(const Epi &e, int n, int b, float v) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                   int num_kb, float *__restrict__ partials, int ldp, Epi epi) {
+                   int num_kb, float *__restrict__ partials, int ldp, Epi epi, KvPrefetch pf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kStages * kStageBytes);
@@ -165,6 +165,8 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     const int nl = q * 32 + lane;  // feature within the tile
     const int n = tile * TM + nl;
     float v[TN];
+    // idle until the accumulator is complete: pull a slice of an upcoming layer's KV cache into L2
+    kv_prefetch(pf, (blockIdx.y * gridDim.x + blockIdx.x) * 4 + q, gridDim.x * gridDim.y * 4);
     pdl_wait();
     if (nkb > 0) {
       mbar_wait(tmem_full, 0);
@@ -402,7 +404,7 @@ static int pick_splits(int tiles, int num_kb) {
 int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, int N, int K, int force_splits,
                        const float *bias, int mode, float *out_f32, bf16 *out_bf16, int64_t ld_out,
                        const QkvScatter *qkv, float *partials, size_t partial_bytes, int *out_splits, int *out_ldp,
-                       bool pdl, cudaStream_t s) {
+                       const KvPrefetch *pf, bool pdl, cudaStream_t s) {
   static const bool cluster_env = getenv("VB_DECODE_CLUSTER") != nullptr;  // opt-in: measured slower (cluster co-scheduling defeats PDL overlap)
   const bool cluster_reduce = cluster_env;
   VB_CHECK_ARG(B >= 1 && B <= dg::TN, "gemm_decode: B=%d not in [1,64]", B);
@@ -455,8 +457,10 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
     if (out_splits) *out_splits = 1;  // nothing left for a consumer to sum
     return VB_OK;
   }
+  KvPrefetch pf0{};
+  if (pf) pf0 = *pf;
   VB_CUDA(launch_kernel(dg::gemm_decode_kernel, dim3(tiles, splits), dim3(dg::kThreads), dg::kSmemBytes, s, pdl, tw,
-                        tx, num_kb, partials, ldp, e));
+                        tx, num_kb, partials, ldp, e, pf0));
   count_launch();
   return VB_OK;
 }

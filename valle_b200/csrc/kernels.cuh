@@ -25,28 +25,31 @@ __device__ __forceinline__ RowMask make_row_mask(int mode, int qr, int L, int S,
   return m;
 }
 
-// L2 prefetch of (part of) the NEXT layer's K or V cache, issued by the small kernels of the decode chain
-// before their dependency wait: the chain is latency bound and leaves HBM idle, the attention kernel that
-// follows is HBM bound -- overlapping the two moves part of its stream into the 126 MB L2.
+// L2 prefetch of a slice of an upcoming layer's K and V cache, issued by the otherwise idle warps of the
+// split-K decode projections (gemm_decode.cu) while their weight tiles stream: the projection chain is latency
+// bound and leaves HBM mostly idle, the KV-cache attention that follows is HBM bound -- the slice [lo_pct, hi_pct)
+// of every (utterance, head) stream is pulled into the 126 MB L2 ahead of it.  Only a hint: the lengths may be
+// one step stale (read before the dependency wait), which changes what is prefetched, never what is computed.
 struct KvPrefetch {
-  const void *base;          // cache of one layer ([B, H, cap, 64]) or nullptr
-  int64_t seq_stride_bytes;  // bytes between utterances
-  int B, H, cap, row_bytes;  // row_bytes = 64 * element size
+  const void *kbase, *vbase;  // caches of the target layer ([B, H, cap, 64]) or nullptr
+  int64_t seq_stride_bytes;   // bytes between utterances
+  int B, H, cap, row_bytes;   // row_bytes = 64 * element size
   const int32_t *text_len, *prompt_len, *n_gen;
-  int pct;                   // percentage of each (b, h) stream to prefetch
+  int lo_pct, hi_pct;
 };
-__device__ __forceinline__ void kv_prefetch(const KvPrefetch &pf) {
-  if (pf.base == nullptr) return;
+// worker = one warp; `n_workers` warps of the grid share the 2 * B * H streams
+__device__ __forceinline__ void kv_prefetch(const KvPrefetch &pf, int worker, int n_workers) {
+  if (pf.kbase == nullptr) return;
   const int lane = threadIdx.x & 31;
-  const int warps_per_cta = blockDim.x >> 5;
-  const int gw = (blockIdx.y * gridDim.x + blockIdx.x) * warps_per_cta + (threadIdx.x >> 5);
-  const int GW = gridDim.x * gridDim.y * warps_per_cta;
-  for (int pair = gw; pair < pf.B * pf.H; pair += GW) {
+  const int n_streams = 2 * pf.B * pf.H;
+  for (int sidx = worker; sidx < n_streams; sidx += n_workers) {
+    const int pair = sidx >> 1;
     const int b = pair / pf.H, h = pair - b * pf.H;
-    int kv = pf.text_len[b] + pf.prompt_len[b] + pf.n_gen[b];
-    kv = min(kv, pf.cap) * pf.pct / 100;
-    const char *p = (const char *)pf.base + (int64_t)b * pf.seq_stride_bytes + (int64_t)h * pf.cap * pf.row_bytes;
-    const int lines = (kv * pf.row_bytes) >> 7;  // 128-byte lines
+    const int kv = min(pf.text_len[b] + pf.prompt_len[b] + pf.n_gen[b], pf.cap);
+    const int r_lo = kv * pf.lo_pct / 100, r_hi = kv * pf.hi_pct / 100;
+    const char *p = (const char *)((sidx & 1) ? pf.vbase : pf.kbase) + (int64_t)b * pf.seq_stride_bytes +
+                    ((int64_t)h * pf.cap + r_lo) * pf.row_bytes;
+    const int lines = ((r_hi - r_lo) * pf.row_bytes) >> 7;  // 128-byte lines
     for (int i = lane; i < lines; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + ((int64_t)i << 7)));
   }
 }
@@ -83,7 +86,7 @@ size_t gemm_decode_workspace();
 int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, int N, int K, int force_splits,
                        const float *bias, int mode, float *out_f32, bf16 *out_bf16, int64_t ld_out,
                        const QkvScatter *qkv, float *partials, size_t partial_bytes, int *out_splits, int *out_ldp,
-                       bool pdl, cudaStream_t s);
+                       const KvPrefetch *pf, bool pdl, cudaStream_t s);
 
 // attention.cu
 int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
@@ -114,10 +117,10 @@ int launch_attn_decode_tma(const float *q, const float *qkv_part, int qkv_splits
 
 // decode_fused.cu
 int launch_relu_reduce(const float *partials, int splits, int ldp, const float *bias, int B, int N, bf16 *out16,
-                       int64_t ldo, const KvPrefetch *pf, bool pdl, cudaStream_t s);
+                       int64_t ldo, bool pdl, cudaStream_t s);
 int launch_ln_reduce(float *x, int64_t ldx, int B, int d, const float *partials, int splits, int ldp,
                      const float *bias, const float *gamma, const float *beta, float eps, bf16 *out16,
-                     const KvPrefetch *pf, bool pdl, cudaStream_t s);
+                     bool pdl, cudaStream_t s);
 
 // sample.cu
 int launch_ar_sample(float *logits, int64_t ld_logits, const float *partials, int splits, int ldp,
