@@ -558,23 +558,41 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
   const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = n_head * HD;
-  pdl_wait();
-  int kv_len = text_len[b] + prompt_len[b] + n_gen[b];
-  kv_len = max(1, min(kv_len, cache_cap));
-  const int pos = kv_len - 1;  // cache row of the current token
-  const int chunk = ((kv_len + nsplit - 1) / nsplit + 15) & ~15;
-  const int c0 = sp * chunk, c1 = min(kv_len, c0 + chunk);
-  const int n = max(0, c1 - c0);
   using T = bf16;
   T *kb = kcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
   T *vb_ = vcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
   const bool has_new = qp.part != nullptr;
   const int g = lane >> 3, j8 = (lane & 7) * 8;
+  // The K rows of earlier tokens and the lengths do not depend on the kernels of THIS step that precede the
+  // launch (the QKV projection only produces the current token), so the chunk geometry is worked out and the
+  // first K batch is requested ahead of the dependency wait; the generated-token count is read again after
+  // the wait and the batch re-requested should it have moved (it cannot when steps are separate graph launches).
+  int kv_len, pos, c0, c1, n;
   uint4 kraw[U];
-  if (n > 0) {
+  auto setup = [&](int n_generated) {
+    kv_len = max(1, min(text_len[b] + prompt_len[b] + n_generated, cache_cap));
+    pos = kv_len - 1;  // cache row of the current token
+    const int chunk = ((kv_len + nsplit - 1) / nsplit + 15) & ~15;
+    c0 = sp * chunk;
+    c1 = min(kv_len, c0 + chunk);
+    n = max(0, c1 - c0);
+    if (n > 0) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) kraw[u] = ldg_stream16(kb + (int64_t)(c0 + min(u * 16 + warp * 4 + g, n - 1)) * HD + j8);
+      for (int u = 0; u < U; ++u)
+        kraw[u] = ldg_stream16(kb + (int64_t)(c0 + min(u * 16 + warp * 4 + g, n - 1)) * HD + j8);
+    }
+  };
+  const int n_gen_early = n_gen[b];
+  setup(n_gen_early);
+  float qbias[3] = {0.f, 0.f, 0.f};
+  if (tid < HD && has_new) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) qbias[j] = qp.bias[j * d + h * HD + tid];
   }
+  pdl_wait();
+  int n_gen_now;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(n_gen_now) : "l"(n_gen + b) : "memory");
+  if (n_gen_now != n_gen_early) setup(n_gen_now);  // uniform over the CTA
   if (tid < HD) {
     if (has_new) {
       float a[3];
@@ -584,7 +602,7 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
         const float *p = qp.part + (int64_t)b * qp.ldp + col;
         float acc = p[0];
         for (int s = 1; s < qp.splits; ++s) acc += p[(int64_t)s * 64 * qp.ldp];
-        a[j] = acc + qp.bias[col];
+        a[j] = acc + qbias[j];
       }
       qs[tid] = a[0] * 0.125f;
       const T k16 = from_f32<T>(a[1]), v16 = from_f32<T>(a[2]);

@@ -18,6 +18,18 @@ ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *
   __shared__ float red[2][8];
   pdl_launch_dependents();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // parameters do not depend on the previous kernel: fetch them ahead of the dependency wait
+  float4 g[kSlabs], be[kSlabs], bb[kSlabs];
+#pragma unroll
+  for (int i = 0; i < kSlabs; ++i) {
+    const int c = (i * 256 + tid) * 4;
+    g[i] = be[i] = bb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < d) {
+      g[i] = *reinterpret_cast<const float4 *>(gamma + c);
+      be[i] = *reinterpret_cast<const float4 *>(beta + c);
+      if (partials && bias) bb[i] = *reinterpret_cast<const float4 *>(bias + c);
+    }
+  }
   pdl_wait();
   float *xr = x + (int64_t)b * ldx;
   float4 v[kSlabs];
@@ -37,8 +49,7 @@ ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *
           a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
         }
         if (bias) {
-          const float4 bb = *reinterpret_cast<const float4 *>(bias + c);
-          a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+          a.x += bb[i].x; a.y += bb[i].y; a.z += bb[i].z; a.w += bb[i].w;
         }
         v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
         *reinterpret_cast<float4 *>(xr + c) = v[i];
@@ -74,10 +85,10 @@ ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *
   for (int i = 0; i < kSlabs; ++i) {
     const int c = (i * 256 + tid) * 4;
     if (c < d) {
-      const float4 g = *reinterpret_cast<const float4 *>(gamma + c);
-      const float4 be = *reinterpret_cast<const float4 *>(beta + c);
-      __nv_bfloat162 p0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + be.x, (v[i].y - mean) * rstd * g.y + be.y);
-      __nv_bfloat162 p1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + be.z, (v[i].w - mean) * rstd * g.w + be.w);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn((v[i].x - mean) * rstd * g[i].x + be[i].x,
+                                                (v[i].y - mean) * rstd * g[i].y + be[i].y);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn((v[i].z - mean) * rstd * g[i].z + be[i].z,
+                                                (v[i].w - mean) * rstd * g[i].w + be[i].w);
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t *>(&p0);
       pk.y = *reinterpret_cast<uint32_t *>(&p1);
@@ -94,6 +105,7 @@ relu_reduce_kernel(const float *__restrict__ partials, int splits, int ldp, cons
   pdl_launch_dependents();
   const int b = blockIdx.y;
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const float4 bb = c < N ? *reinterpret_cast<const float4 *>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);  // ahead of the wait
   pdl_wait();
   if (c >= N) return;
   const float *p = partials + (int64_t)b * ldp + c;
@@ -103,7 +115,6 @@ relu_reduce_kernel(const float *__restrict__ partials, int splits, int ldp, cons
     const float4 t = __ldcg(reinterpret_cast<const float4 *>(p + (int64_t)s * 64 * ldp));
     a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
   }
-  const float4 bb = *reinterpret_cast<const float4 *>(bias + c);
   __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(a.x + bb.x, 0.f), fmaxf(a.y + bb.y, 0.f));
   __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(a.z + bb.z, 0.f), fmaxf(a.w + bb.w, 0.f));
   uint2 pk;

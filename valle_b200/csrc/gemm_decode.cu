@@ -405,8 +405,12 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
                        const float *bias, int mode, float *out_f32, bf16 *out_bf16, int64_t ld_out,
                        const QkvScatter *qkv, float *partials, size_t partial_bytes, int *out_splits, int *out_ldp,
                        const KvPrefetch *pf, bool pdl, cudaStream_t s) {
-  static const bool cluster_env = getenv("VB_DECODE_CLUSTER") != nullptr;  // opt-in: measured slower (cluster co-scheduling defeats PDL overlap)
-  const bool cluster_reduce = cluster_env;
+  // opt-in, measured slower when applied to every projection (cluster co-scheduling defeats PDL overlap):
+  // VB_DECODE_CLUSTER=1 -> all modes, VB_DECODE_CLUSTER_MODES=<bitmask of DG_* modes> -> selected projections
+  static const int cluster_mask = getenv("VB_DECODE_CLUSTER") != nullptr
+                                      ? 0xf
+                                      : (getenv("VB_DECODE_CLUSTER_MODES") ? atoi(getenv("VB_DECODE_CLUSTER_MODES")) : 0);
+  const bool cluster_reduce = ((cluster_mask >> mode) & 1) != 0;
   VB_CHECK_ARG(B >= 1 && B <= dg::TN, "gemm_decode: B=%d not in [1,64]", B);
   VB_CHECK_ARG(K % tc::BK == 0 && ld_act % 8 == 0, "gemm_decode: K %% 64 != 0 or unaligned activations");
   const int tiles = (N + dg::TM - 1) / dg::TM;

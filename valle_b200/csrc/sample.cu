@@ -46,20 +46,47 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
   pdl_launch_dependents();
   pdl_wait();
   if (finished[b] != 0 && !reduce_only) return;  // uniform per CTA
+  // scalars of the stop rule: in flight together with the logits instead of after the argmax
+  const int n_new = n_gen[b], p_len = prompt_len[b], cap_new = max_new[b];
+  const int forced_tok = forced ? (int)forced[b] : -1;
   float *row = logits + (int64_t)b * ld_logits;
   ArgMax best{-CUDART_INF_F, 0x7fffffff};
-  for (int i = tid; i < n_vocab; i += 256) {
-    float v;
-    if (partials) {  // split-K partials of the head projection, summed in fixed order
-      const float *p = partials + (int64_t)b * ldp + i;
-      v = __ldcg(p);
-#pragma unroll 8
-      for (int s = 1; s < splits; ++s) v += __ldcg(p + (int64_t)s * 64 * ldp);
-      row[i] = v;
-    } else {
-      v = row[i];
+  if (partials && n_vocab <= 5 * 256 && splits <= 8) {
+    // head projection split-K partials, summed in fixed order; all loads of the row issued at once
+    float v[5][8];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int i = tid + j * 256;
+      const float *p = partials + (int64_t)b * ldp + min(i, n_vocab - 1);
+#pragma unroll
+      for (int s = 0; s < 8; ++s) v[j][s] = s < splits ? __ldcg(p + (int64_t)s * 64 * ldp) : 0.f;
     }
-    best = better(best, ArgMax{v, i});
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int i = tid + j * 256;
+      float a = v[j][0];
+#pragma unroll
+      for (int s = 1; s < 8; ++s)
+        if (s < splits) a += v[j][s];
+      if (i < n_vocab) {
+        row[i] = a;
+        best = better(best, ArgMax{a, i});
+      }
+    }
+  } else {
+    for (int i = tid; i < n_vocab; i += 256) {
+      float v;
+      if (partials) {
+        const float *p = partials + (int64_t)b * ldp + i;
+        v = __ldcg(p);
+#pragma unroll 8
+        for (int s = 1; s < splits; ++s) v += __ldcg(p + (int64_t)s * 64 * ldp);
+        row[i] = v;
+      } else {
+        v = row[i];
+      }
+      best = better(best, ArgMax{v, i});
+    }
   }
   if (reduce_only) return;
   best = warp_argmax(best);
@@ -69,9 +96,8 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
     ArgMax a = wbest[0];
 #pragma unroll
     for (int w = 1; w < 8; ++w) a = better(a, wbest[w]);
-    const int n_new = n_gen[b];
-    const int samp = forced ? (int)forced[b] : a.i;
-    const bool stop = (a.i == eos_id) || (samp == eos_id) || (n_new > max_new[b]) || (n_new >= tok_stride);
+    const int samp = forced ? forced_tok : a.i;
+    const bool stop = (a.i == eos_id) || (samp == eos_id) || (n_new > cap_new) || (n_new >= tok_stride);
     if (stop) {
       finished[b] = (n_new == 0) ? 2 : 1;
       s_tok = -1;
@@ -79,7 +105,7 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
       tokens[(int64_t)b * tok_stride + n_new] = samp;
       n_gen[b] = n_new + 1;
       s_tok = samp;
-      s_pos = min(prompt_len[b] + n_new, pe_rows - 1);
+      s_pos = min(p_len + n_new, pe_rows - 1);
     }
   }
   __syncthreads();
