@@ -22,6 +22,7 @@ import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -105,6 +106,18 @@ class _ArView:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.graph_key = None
         self.graph_kernels = 0
+
+
+def _seg_ranges(starts, lens):
+    """Concatenated aranges: rows = [starts[b] + i for b for i in range(lens[b])], pos = the i's (int64 numpy)."""
+    starts = np.asarray(starts, dtype=np.int64)
+    lens = np.asarray(lens, dtype=np.int64)
+    total = int(lens.sum())
+    if total == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    seg_first = np.repeat(np.cumsum(lens) - lens, lens)
+    pos = np.arange(total, dtype=np.int64) - seg_first
+    return np.repeat(starts, lens) + pos, pos
 
 
 class ValleEngine:
@@ -210,14 +223,11 @@ class ValleEngine:
         for n in seq_len:
             cu.append(cu[-1] + n)
         M = cu[-1]
-        text_rows, text_pos, aud_rows, aud_pos = [], [], [], []
-        for b in range(B):
-            text_rows += range(cu[b], cu[b] + S[b])
-            text_pos += range(S[b])
-            aud_rows += range(cu[b] + S[b], cu[b + 1])
-            aud_pos += range(Tp[b])
-        meta = torch.tensor(cu + S + Tp + cap_new + text_rows + text_pos + aud_rows + aud_pos
-                            + [c - 1 for c in cu[1:]], dtype=torch.int32).to(dev, non_blocking=True)
+        cu_np = np.asarray(cu, dtype=np.int64)
+        text_rows, text_pos = _seg_ranges(cu_np[:-1], S)
+        aud_rows, aud_pos = _seg_ranges(cu_np[:-1] + np.asarray(S, dtype=np.int64), Tp)
+        meta = torch.from_numpy(np.concatenate([cu_np, S, Tp, cap_new, text_rows, text_pos, aud_rows, aud_pos,
+                                                cu_np[1:] - 1]).astype(np.int32)).to(dev, non_blocking=True)
         o = 0
         def take(n):
             nonlocal o
@@ -288,7 +298,7 @@ class ValleEngine:
             cu_g.append(cu_g[-1] + n)
         G = cu_g[-1]
         codes = torch.empty((G, Q), dtype=torch.int64, device=dev)
-        src = torch.tensor([b * tok_stride + i for b in range(B) for i in range(Tg[b])], dtype=torch.int64, device=dev)
+        src = torch.from_numpy(_seg_ranges(np.arange(B, dtype=np.int64) * tok_stride, Tg)[0]).to(dev)
         codes[:, 0] = buf.tokens.view(-1).index_select(0, src).to(torch.int64)
         if Q > 1:
             self._nar(texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, enroll_lens)
@@ -441,16 +451,16 @@ class ValleEngine:
         cu_p = [0]
         for n in Tp:
             cu_p.append(cu_p[-1] + n)
-        # index maps (host-built, one H2D)
-        trow, tpos, yrow, ypos, y_prompt_rows, y_gen_rows, tgt_rows = [], [], [], [], [], [], []
-        for b in range(B):
-            trow += range(cu[b], cu[b] + S2[b]); tpos += range(S2[b])
-            yrow += range(cu[b] + S2[b], cu[b + 1]); ypos += range(T[b])
-            y_prompt_rows += range(cu_t[b], cu_t[b] + Tp[b])
-            y_gen_rows += range(cu_t[b] + Tp[b], cu_t[b + 1])
-            tgt_rows += range(cu[b] + S2[b] + Tp[b], cu[b + 1])
-        meta = torch.tensor(cu + trow + tpos + yrow + ypos + y_prompt_rows + y_gen_rows + tgt_rows,
-                            dtype=torch.int32).to(dev)
+        # index maps (host-built with numpy, one H2D)
+        cu_np, cut_np = np.asarray(cu, dtype=np.int64), np.asarray(cu_t, dtype=np.int64)
+        S2_np, Tp_np = np.asarray(S2, dtype=np.int64), np.asarray(Tp, dtype=np.int64)
+        trow, tpos = _seg_ranges(cu_np[:-1], S2)
+        yrow, ypos = _seg_ranges(cu_np[:-1] + S2_np, T)
+        y_prompt_rows = _seg_ranges(cut_np[:-1], Tp)[0]
+        y_gen_rows = _seg_ranges(cut_np[:-1] + Tp_np, Tg)[0]
+        tgt_rows = _seg_ranges(cu_np[:-1] + S2_np + Tp_np, Tg)[0]
+        meta = torch.from_numpy(np.concatenate([cu_np, trow, tpos, yrow, ypos, y_prompt_rows, y_gen_rows,
+                                                tgt_rows]).astype(np.int32)).to(dev)
         o = 0
         def take(n):
             nonlocal o
