@@ -582,8 +582,10 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
         kraw[u] = ldg_stream16(kb + (int64_t)(c0 + min(u * 16 + warp * 4 + g, n - 1)) * HD + j8);
     }
   };
-  const int n_gen_early = n_gen[b];
-  setup(n_gen_early);
+  // (only with the fused QKV prologue: there the current token's row is served from shared memory; without it the
+  // row was written to the cache by the kernel this launch depends on and nothing may be read ahead of the wait)
+  const int n_gen_early = has_new ? n_gen[b] : -1;
+  if (has_new) setup(n_gen_early);
   float qbias[3] = {0.f, 0.f, 0.f};
   if (tid < HD && has_new) {
 #pragma unroll

@@ -27,11 +27,12 @@ using namespace tc;
 
 constexpr int TM = 128;      // weight rows per tile (UMMA M)
 constexpr int TN = 64;       // activation rows (UMMA N)
-constexpr int kStages = 6;
+constexpr int kStagesMax = 6;  // pipeline depth is a template parameter (6, or 3 to leave room for a co-resident kernel)
 constexpr int kWBytes = TM * BK * 2;  // 16 KB
 constexpr int kXBytes = TN * BK * 2;  // 8 KB
 constexpr int kStageBytes = kWBytes + kXBytes;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024 + 256; }
+constexpr int kSmemBytes = smem_bytes(kStagesMax);
 constexpr int kThreads = 256;
 constexpr int kTmemCols = 64;
 
@@ -72,7 +73,8 @@ __device__ __forceinline__ void apply_epi(const Epi &e, int n, int b, float v) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kStages>
+__global__ void __launch_bounds__(kThreads) __maxnreg__(kStages == 3 ? 96 : 208)
 gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                    int num_kb, float *__restrict__ partials, int ldp, Epi epi, KvPrefetch pf) {
   extern __shared__ uint8_t smem_raw[];
@@ -439,8 +441,10 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
   }
   static bool attr_set = false;
   if (!attr_set) {
-    VB_CUDA(cudaFuncSetAttribute(dg::gemm_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 dg::kSmemBytes));
+    VB_CUDA(cudaFuncSetAttribute(dg::gemm_decode_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 dg::smem_bytes(6)));
+    VB_CUDA(cudaFuncSetAttribute(dg::gemm_decode_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 dg::smem_bytes(3)));
     VB_CUDA(cudaFuncSetAttribute(dg::gemm_decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  dg::kSmemBytesC));
     attr_set = true;
@@ -463,8 +467,14 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
   }
   KvPrefetch pf0{};
   if (pf) pf0 = *pf;
-  VB_CUDA(launch_kernel(dg::gemm_decode_kernel, dim3(tiles, splits), dim3(dg::kThreads), dg::kSmemBytes, s, pdl, tw,
-                        tx, num_kb, partials, ldp, e, pf0));
+  // a 3-stage ring (72 KB) leaves shared memory for the KV-cache attention CTAs of a second micro-batch stream
+  static const bool shallow = getenv("VB_DECODE_GEMM_STAGES") && atoi(getenv("VB_DECODE_GEMM_STAGES")) == 3;
+  if (shallow)
+    VB_CUDA(launch_kernel(dg::gemm_decode_kernel<3>, dim3(tiles, splits), dim3(dg::kThreads), dg::smem_bytes(3), s, pdl,
+                          tw, tx, num_kb, partials, ldp, e, pf0));
+  else
+    VB_CUDA(launch_kernel(dg::gemm_decode_kernel<6>, dim3(tiles, splits), dim3(dg::kThreads), dg::smem_bytes(6), s, pdl,
+                          tw, tx, num_kb, partials, ldp, e, pf0));
   count_launch();
   return VB_OK;
 }
