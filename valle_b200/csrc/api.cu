@@ -140,6 +140,8 @@ struct StepWs {
   bf16 *xn16, *att16, *hb16;
   void *gemm_ws;
   size_t gemm_ws_bytes;
+  void *persist;   // scratch of the persistent small-batch step (decode_persistent.cu)
+  unsigned *sync;  // its two grid-barrier words (zero-initialised by the caller's workspace allocation)
   size_t total;
 };
 StepWs carve_step_ws(const vb_decoder_desc &D, int B, int cache_cap, void *base) {
@@ -160,6 +162,8 @@ StepWs carve_step_ws(const vb_decoder_desc &D, int B, int cache_cap, void *base)
   w.hb16 = (bf16 *)take((size_t)64 * dff * 2);
   w.gemm_ws_bytes = gemm_decode_workspace();
   w.gemm_ws = take(w.gemm_ws_bytes);
+  w.persist = take(B <= 4 ? persistent_step_workspace(D, B) : 0);
+  w.sync = (unsigned *)take(256);
   w.total = (size_t)(p - (char *)base) + 256;
   return w;
 }
@@ -241,6 +245,8 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
   const size_t ts = elem_size(dt);
   StepWs w = carve_step_ws(D, B, st->cache_cap, workspace);
   float *x = st->x_cur;
+  if (head->greedy && persistent_step_supported(D, B, st->cache_cap))
+    return launch_persistent_step(D, dec->layers, head, st, w.persist, w.sync, s);
   if (use_tc_decode(D, B)) {
     // bf16 tensor-core path: LayerNorm(+pending residual) -> swap-AB split-K tcgen05 projections whose
     // partial sums are consumed by the next kernel in the chain (7 launches per layer, PDL-chained)

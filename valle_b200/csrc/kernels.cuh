@@ -88,6 +88,12 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
                        const QkvScatter *qkv, float *partials, size_t partial_bytes, int *out_splits, int *out_ldp,
                        const KvPrefetch *pf, bool pdl, cudaStream_t s);
 
+// decode_persistent.cu (one cooperative kernel per AR decode step for 1..4 utterances, bf16)
+bool persistent_step_supported(const vb_decoder_desc &D, int B, int cache_cap);
+size_t persistent_step_workspace(const vb_decoder_desc &D, int B);
+int launch_persistent_step(const vb_decoder_desc &D, const vb_layer_params *layers, const vb_ar_head *head,
+                           vb_ar_state *st, void *scratch, unsigned *sync, cudaStream_t s);
+
 // attention.cu
 int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
                             const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,
