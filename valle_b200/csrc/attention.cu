@@ -380,168 +380,10 @@ attn_decode_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *_
   }
 }
 
-// two-phase variant (scores of the whole chunk to shared memory, block softmax, then P.V)
-template <typename T, int U>
-__global__ void __launch_bounds__(128)
-attn_decode_2phase_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *__restrict__ kcache,
-                   T *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
-                   const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
-                   const int32_t *__restrict__ n_gen, float *__restrict__ out, bf16 *__restrict__ out16,
-                   float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit) {
-  __shared__ float sc[kDecMaxChunk];
-  __shared__ __align__(16) float qs[HD];
-  __shared__ __align__(16) float knew[HD];
-  __shared__ __align__(16) float vnew[HD];
-  __shared__ float red[16][HD + 1];
-  __shared__ float wred[8];
-  pdl_launch_dependents();
-  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int d = n_head * HD;
-  pdl_wait();
-  int kv_len = text_len[b] + prompt_len[b] + n_gen[b];
-  kv_len = max(1, min(kv_len, cache_cap));
-  const int pos = kv_len - 1;  // cache row of the current token
-  const int chunk = ((kv_len + nsplit - 1) / nsplit + 15) & ~15;
-  const int c0 = sp * chunk, c1 = min(kv_len, c0 + chunk);
-  const int n = max(0, c1 - c0);
-  T *kb = kcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
-  T *vb_ = vcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
-  const bool has_new = qp.part != nullptr;
-  if (tid < HD) {
-    if (has_new) {
-      float a[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int col = j * d + h * HD + tid;
-        const float *p = qp.part + (int64_t)b * qp.ldp + col;
-        float acc = p[0];
-        for (int s = 1; s < qp.splits; ++s) acc += p[(int64_t)s * 64 * qp.ldp];
-        a[j] = acc + qp.bias[col];
-      }
-      qs[tid] = a[0] * 0.125f;
-      const T k16 = from_f32<T>(a[1]), v16 = from_f32<T>(a[2]);
-      knew[tid] = to_f32(k16);  // exactly what later steps will read back from the cache
-      vnew[tid] = to_f32(v16);
-      if (sp == 0) {
-        kb[(int64_t)pos * HD + tid] = k16;
-        vb_[(int64_t)pos * HD + tid] = v16;
-      }
-    } else {
-      qs[tid] = q[(int64_t)b * d + h * HD + tid] * 0.125f;
-    }
-  }
-  __syncthreads();
-
-  // ---- scores: 8 lanes per key, 4 keys per warp-iteration, 16 keys per CTA-iteration ----
-  const int g = lane >> 3, j8 = (lane & 7) * 8;
-  float qf[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) qf[i] = qs[j8 + i];
-  float lmax = -CUDART_INF_F;
-  const bool new_here = has_new && pos >= c0 && pos < c1;  // the current token's key lives in smem
-  for (int base = 0; base < n; base += 16 * U) {
-    float kf[U][8];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int key = base + u * 16 + warp * 4 + g;
-      const int kk = min(key, n - 1);
-      KvRow8<T>::load(kb + (int64_t)(c0 + kk) * HD + j8, kf[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int key = base + u * 16 + warp * 4 + g;
-      float dot = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], kf[u][i], dot);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-      dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-      if ((lane & 7) == 0 && key < n && !(new_here && c0 + key == pos)) {
-        sc[key] = dot;
-        lmax = fmaxf(lmax, dot);
-      }
-    }
-  }
-  if (new_here && warp == 0) {  // score of the current token from the shared-memory key (never from the cache)
-    float dot = 0.f;
-    if (lane < 8) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], knew[j8 + i], dot);
-    }
-    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    if (lane == 0) {
-      sc[pos - c0] = dot;
-      lmax = fmaxf(lmax, dot);
-    }
-  }
-  lmax = warp_max(lmax);
-  if (lane == 0) wred[warp] = lmax;
-  __syncthreads();
-  const float m = fmaxf(fmaxf(wred[0], wred[1]), fmaxf(wred[2], wred[3]));
-  float lsum = 0.f;
-  for (int i = tid; i < n; i += 128) {
-    const float p = expf(sc[i] - m);
-    sc[i] = p;
-    lsum += p;
-  }
-  lsum = warp_sum(lsum);
-  if (lane == 0) wred[4 + warp] = lsum;
-  __syncthreads();
-  const float l = (wred[4] + wred[5]) + (wred[6] + wred[7]);
-
-  // ---- O = P V : thread = (element group eg, key lane jl) --------------------------------
-  const int eg = (tid & 7) * 8, jl = tid >> 3;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int base = 0; base < n; base += 16 * U) {
-    float vf[U][8];
-    float pv[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int key = base + u * 16 + jl;
-      const int kk = min(key, n - 1);
-      pv[u] = (key < n && !(new_here && c0 + key == pos)) ? sc[kk] : 0.f;
-      KvRow8<T>::load(vb_ + (int64_t)(c0 + kk) * HD + eg, vf[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(pv[u], vf[u][i], acc[i]);
-  }
-  if (new_here && jl == 0) {
-    const float pn = sc[pos - c0];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pn, vnew[eg + i], acc[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) red[jl][eg + i] = acc[i];
-  __syncthreads();
-  if (tid < HD) {
-    float s = 0.f;
-#pragma unroll
-    for (int r = 0; r < 16; ++r) s += red[r][tid];
-    if (nsplit == 1) {
-      out[(int64_t)b * d + h * HD + tid] = s / l;
-      if (out16) out16[(int64_t)b * d + h * HD + tid] = __float2bfloat16_rn(s / l);
-    } else {
-      const int64_t pi = ((int64_t)b * n_head + h) * nsplit + sp;
-      part_o[pi * HD + tid] = s;
-      if (tid == 0) {
-        part_ml[pi * 2] = n > 0 ? m : -CUDART_INF_F;
-        part_ml[pi * 2 + 1] = n > 0 ? l : 0.f;
-      }
-    }
-  }
-}
-
-// bf16 two-phase variant with the FIRST batch of K rows fetched ahead of the q/k/v prologue and the first batch
-// of V rows fetched ahead of the block softmax: all CTAs of the single wave run their phases in lock step, so
+// bf16 two-phase kernel (scores of the whole chunk to shared memory, block softmax, then P.V) with the FIRST batch
+// of K rows fetched ahead of the q/k/v prologue and the first batch of V rows fetched ahead of the block softmax: all CTAs of the single wave run their phases in lock step, so
 // without this the HBM pipe idles through every prologue / softmax / epilogue of the launch.
-template <int U, bool kPipe>
+template <int U>
 __global__ void __launch_bounds__(128, 7)
 attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, bf16 *__restrict__ kcache,
                    bf16 *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
@@ -627,14 +469,7 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
   float lmax = -CUDART_INF_F;
   const bool new_here = has_new && pos >= c0 && pos < c1;  // the current token's key lives in smem
   for (int base = 0; base < n; base += 16 * U) {
-    uint4 knext[U];
-    if (kPipe) {  // the next batch is in flight while this one is scored
-      if (base + 16 * U < n) {
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          knext[u] = ldg_stream16(kb + (int64_t)(c0 + min(base + 16 * U + u * 16 + warp * 4 + g, n - 1)) * HD + j8);
-      }
-    } else if (base > 0) {
+    if (base > 0) {
 #pragma unroll
       for (int u = 0; u < U; ++u)
         kraw[u] = ldg_stream16(kb + (int64_t)(c0 + min(base + u * 16 + warp * 4 + g, n - 1)) * HD + j8);
@@ -656,10 +491,6 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
         sc[key] = dot;
         lmax = fmaxf(lmax, dot);
       }
-    }
-    if (kPipe && base + 16 * U < n) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) kraw[u] = knext[u];
     }
   }
   // first batch of V rows in flight across the block softmax
@@ -703,14 +534,7 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   for (int base = 0; base < n; base += 16 * U) {
-    uint4 vnext[U];
-    if (kPipe) {
-      if (base + 16 * U < n) {
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          vnext[u] = ldg_stream16(vb_ + (int64_t)(c0 + min(base + 16 * U + u * 16 + jl, n - 1)) * HD + eg);
-      }
-    } else if (base > 0) {
+    if (base > 0) {
 #pragma unroll
       for (int u = 0; u < U; ++u)
         vraw[u] = ldg_stream16(vb_ + (int64_t)(c0 + min(base + u * 16 + jl, n - 1)) * HD + eg);
@@ -725,10 +549,6 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
       v.unpack(vf);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = fmaf(pv, vf[i], acc[i]);
-    }
-    if (kPipe && base + 16 * U < n) {
-#pragma unroll
-      for (int u = 0; u < U; ++u) vraw[u] = vnext[u];
     }
   }
   if (new_here && jl == 0) {
@@ -804,35 +624,20 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
   float *part_ml = part_o + (size_t)B * n_head * ns * HD;
   QkvPartials qp{qkv_part, qkv_bias, qkv_splits, qkv_ldp};
   dim3 grid(n_head, B, ns);
-  if (dtype == VB_BF16 && getenv("VB_ATTN_DECODE_TMA") != nullptr)  // opt-in: cp.async.bulk ring variant
-    VB_TRY(launch_attn_decode_tma(q, qkv_part, qkv_splits, qkv_ldp, qkv_bias, B, n_head, kcache, vcache,
-                                  cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out, out16, part_o, part_ml,
-                                  ns, pdl, s));
-  else if (dtype == VB_F32)
-    VB_CUDA(launch_kernel(attn_decode_kernel<float>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (float *)kcache,
-                          (float *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
-                          (bf16 *)out16, part_o, part_ml, ns));
-  else if (getenv("VB_ATTN_DECODE_1PASS") == nullptr && getenv("VB_ATTN_DECODE_NOPF") == nullptr)  // default
-  {
-    static const int pipe = getenv("VB_ATTN_DECODE_PIPE") ? atoi(getenv("VB_ATTN_DECODE_PIPE")) : 0;
-    auto kern = pipe == 4 ? attn_decode_2phase_pf_kernel<4, true>
-                          : pipe == 6 ? attn_decode_2phase_pf_kernel<6, true> : attn_decode_2phase_pf_kernel<8, false>;
-    VB_CUDA(launch_kernel(kern, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache, (bf16 *)vcache,
-                          cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out, (bf16 *)out16, part_o, part_ml,
-                          ns));
+  if (dtype == VB_F32 || getenv("VB_ATTN_DECODE_1PASS") != nullptr) {  // fp32 parity path / single-pass variant
+    if (dtype == VB_F32)
+      VB_CUDA(launch_kernel(attn_decode_kernel<float>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (float *)kcache,
+                            (float *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
+                            (bf16 *)out16, part_o, part_ml, ns));
+    else
+      VB_CUDA(launch_kernel(attn_decode_kernel<bf16>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
+                            (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
+                            (bf16 *)out16, part_o, part_ml, ns));
+  } else {
+    VB_CUDA(launch_kernel(attn_decode_2phase_pf_kernel<8>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
+                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out, (bf16 *)out16,
+                          part_o, part_ml, ns));
   }
-  else if (getenv("VB_ATTN_DECODE_1PASS") == nullptr && getenv("VB_ATTN_DECODE_U4") != nullptr)
-    VB_CUDA(launch_kernel(attn_decode_2phase_kernel<bf16, 4>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
-                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
-                          (bf16 *)out16, part_o, part_ml, ns));
-  else if (getenv("VB_ATTN_DECODE_1PASS") == nullptr)
-    VB_CUDA(launch_kernel(attn_decode_2phase_kernel<bf16, 8>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
-                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
-                          (bf16 *)out16, part_o, part_ml, ns));
-  else
-    VB_CUDA(launch_kernel(attn_decode_kernel<bf16>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
-                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
-                          (bf16 *)out16, part_o, part_ml, ns));
   count_launch();
   if (ns > 1) {
     VB_CUDA(launch_kernel(attn_decode_combine_kernel, dim3(n_head, B), dim3(HD), 0, s, pdl, (const float *)part_o,

@@ -3,20 +3,14 @@
 // (F.multi_head_attention_forward, valle/modules/activation.py:408-427; no mask for NAR
 // valle/models/valle.py:1125-1127, key-padding / causal rules of valle.py:835-861,921-925).
 //
-// One CTA = 128 query rows of one (sequence, head); 192 threads:
+// One CTA = 128 query rows of one (sequence, head); 320 threads:
 //   warp 0    TMA producer: Q tile once, then K and V tiles (128 keys x 64, 128B-swizzle boxes of the
 //             packed [M, 3d] qkv matrix) through a 2-stage mbarrier ring
-//   warp 1    MMA issuer:  S = Q K^T  (tcgen05.mma M=128, N=128, K=16 x4, fp32 in TMEM columns 0..127)
-//                          O_t = P V   (M=128, N=64, K=16 x8, TMEM columns 128..191; P from shared
-//                          memory as the K-major A operand, V as an MN-major B operand -- the V tile
-//                          is used exactly as TMA lands it, no transpose)
-//   warps 2-9 softmax: TWO THREADS OWN ONE QUERY ROW (TMEM lane): warps 2-5 take score columns 0..63 and
-//             output dims 0..31, warps 6-9 columns 64..127 and dims 32..63; the row maximum is the only
-//             thing the pair exchanges (shared memory + a 64-thread named barrier).
-//             p = exp2(s*c - m) -> bf16 -> swizzled shared memory (A operand of P V); after the P V MMA
-//             each thread folds its half of O_t into its fp32 accumulator with the online-softmax correction.
-// QK^T of tile j+1 is issued right after P V of tile j, so the tensor pipe works while the softmax
-// threads fold O_t; two CTAs fit per SM (112 KB smem, 256 TMEM columns each) and interleave.
+//   warp 1    MMA issuer (one elected thread), tcgen05.mma with fp32 accumulators in TMEM; V is used as an
+//             MN-major B operand exactly as TMA lands it, no transpose
+//   warps 2-9 two softmax groups of 4 warps, one thread per query row (TMEM lane) -- see the pipeline
+//             description above attn_tcgen05_pp_kernel
+// two CTAs fit per SM (112 KB smem, 256 TMEM columns each) and interleave.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -29,15 +23,15 @@ namespace fa5 {
 using namespace tc;
 
 constexpr int HD = 64, BQ = 128, BKV = 128;
-constexpr int kThreads = 320;  // TMA warp, MMA warp, 8 softmax warps (two threads per query row)
+constexpr int kThreads = 320;  // TMA warp, MMA warp, 2 x 4 softmax warps
 constexpr int kQBytes = BQ * HD * 2;         // 16 KB
 constexpr int kKBytes = BKV * HD * 2;        // 16 KB
 constexpr int kStageBytes = 2 * kKBytes;     // K + V
 constexpr int kStages = 2;
 constexpr int kPBytes = BQ * BKV * 2;        // 32 KB (two 64-key K-blocks of [128 x 64])
-constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kPBytes + 96 + 512;  // barriers + xch
+constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kPBytes + 96 + 512;  // + barriers, TMEM slot
 static_assert(2 * (kSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM must fit");
-constexpr int kTmemCols = 256;               // S: 128 cols, O_t: 64 cols
+constexpr int kTmemCols = 256;               // S_0, S_1, O_0, O_1: 64 columns each
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -58,7 +52,6 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
 // instruction descriptor with B MN-major (bit 16)
 __host__ __device__ constexpr uint32_t make_idesc_bmn(int M, int N) { return make_idesc(M, N) | (1u << 16); }
 
-// row maximum of this thread's 64 raw scores (thread = TMEM lane, column half `hf`)
 // chunk-local visibility of 32 consecutive keys starting at key index cb:
 // valid(i) = i < a  or  b0 <= i < b1   (the two segments of RowMask clamped to the chunk)
 struct ChunkMask {
@@ -73,7 +66,7 @@ struct ChunkMask {
   __device__ __forceinline__ bool ok(int i) const { return i < a || (i >= b0 && i < b1); }
 };
 
-// row maximum of this thread's 64 raw scores (thread = TMEM lane, column half `hf`)
+// row maximum of this thread's 64 raw scores (thread = TMEM lane = query row, score buffer of its group)
 template <bool kMask>
 __device__ __forceinline__ float half_row_max(uint32_t taddr, const RowMask &rm, int jc0) {
   float mx = -CUDART_INF_F;
@@ -153,256 +146,8 @@ __device__ __forceinline__ float half_row_p(uint32_t taddr, const RowMask &rm, i
   return rs;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
-attn_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, const int32_t *__restrict__ cu_seqlens,
-                    const int32_t *__restrict__ text_lens, const int32_t *__restrict__ seg1_lens, int seg1_start,
-                    int mask_mode, bf16 *__restrict__ out, int skip_partial) {
-  extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t *sQ = smem;
-  uint8_t *sKV = sQ + kQBytes;                       // [stage][K | V]
-  uint8_t *sP = sKV + kStages * kStageBytes;         // [2 k-blocks][128 rows x 128 B]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + kPBytes);
-  uint64_t *q_full = bars;              // 1
-  uint64_t *kv_full = bars + 1;         // [kStages]
-  uint64_t *kv_empty = kv_full + kStages;
-  uint64_t *s_full = kv_empty + kStages;   // S ready in TMEM
-  uint64_t *p_full = s_full + 1;           // P in smem, S consumed (4 warp arrivals)
-  uint64_t *o_full = p_full + 1;           // O_t ready in TMEM
-  uint64_t *o_empty = o_full + 1;          // O_t consumed, P buffer free (4 warp arrivals)
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 1);
-  float *xch = reinterpret_cast<float *>(tmem_slot + 2);  // [128 rows] pair exchange slot
-
-  const int b = blockIdx.z, h = blockIdx.y;
-  const int r0 = cu_seqlens[b], L = cu_seqlens[b + 1] - r0;
-  // skip_partial == 1: ragged tail rows go to the 64-row warp-level kernel.
-  // skip_partial == 2: the last tile is shifted back to rows [L - 128, L): it overlaps its predecessor, the
-  //   overlapping rows are recomputed bit-identically (rows are independent) and stored twice.
-  int q0 = blockIdx.x * BQ;
-  if (q0 >= L) return;
-  if (q0 + BQ > L) {
-    if (skip_partial == 1) return;
-    if (skip_partial == 2 && L >= BQ) q0 = L - BQ;
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d = n_head * HD;
-  const int S = (mask_mode != VB_MASK_FULL) ? text_lens[b] : 0;
-  const int c1 = (mask_mode >= VB_MASK_PADDED_AR) ? seg1_lens[b] : 0;
-  const int q_hi = min(q0 + BQ, L);
-  const int kv_max = (mask_mode == VB_MASK_VALLE_AR) ? max(S, q_hi) : L;
-  const int n_tiles = (kv_max + BKV - 1) / BKV;
-
-  if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
-  if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 8);   // one arrival per softmax warp
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 8);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(kTmemCols));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128;
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      mbar_expect_tx(q_full, kQBytes);
-      tma_load_2d(&tmap, q_full, sQ, h * HD, r0 + q0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t *dst = sKV + stage * kStageBytes;
-        mbar_expect_tx(&kv_full[stage], kStageBytes);
-        tma_load_2d(&tmap, &kv_full[stage], dst, d + h * HD, r0 + t * BKV);
-        tma_load_2d(&tmap, &kv_full[stage], dst + kKBytes, 2 * d + h * HD, r0 + t * BKV);
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(BQ, BKV);      // S = Q K^T : both K-major
-      constexpr uint32_t idesc_o = make_idesc_bmn(BQ, HD);   // O_t = P V : A K-major, B MN-major
-      const uint64_t qdesc = make_smem_desc(smem_u32(sQ));
-      const uint64_t pdesc0 = make_smem_desc(smem_u32(sP));
-      mbar_wait(q_full, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      // prologue: S(0)
-      mbar_wait(&kv_full[0], 0);
-      tcgen05_fence_after();
-      {
-        const uint64_t kdesc = make_smem_desc(smem_u32(sKV));
-#pragma unroll
-        for (int k = 0; k < HD / UMMA_K; ++k) umma_bf16(tmem_s, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
-        tcgen05_commit(s_full);
-      }
-      for (int t = 0; t < n_tiles; ++t) {
-        mbar_wait(p_full, t & 1);                 // P(t) written, S(t) consumed
-        tcgen05_fence_after();
-        const int vstage = stage;
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
-        // ---- S(t+1) = Q K(t+1)^T first: the softmax threads wait on it, P V runs behind it ----
-        if (t + 1 < n_tiles) {
-          mbar_wait(&kv_full[stage], phase);
-          tcgen05_fence_after();
-          const uint64_t kdesc = make_smem_desc(smem_u32(sKV + stage * kStageBytes));
-#pragma unroll
-          for (int k = 0; k < HD / UMMA_K; ++k) umma_bf16(tmem_s, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
-          tcgen05_commit(s_full);
-        }
-        // ---- O_t = P(t) V(t) ----
-        if (t > 0) {
-          mbar_wait(o_empty, (t - 1) & 1);        // O_t(t-1) folded
-          tcgen05_fence_after();
-        }
-        const uint32_t v_addr = smem_u32(sKV + vstage * kStageBytes + kKBytes);
-        const uint64_t vdesc = make_smem_desc_mn(v_addr);
-#pragma unroll
-        for (int k = 0; k < BKV / UMMA_K; ++k) {
-          // A: P k-block (k / 4), +32 B per 16 keys inside the 64-key swizzle atom
-          const uint64_t pd = pdesc0 + (uint64_t)((k >> 2) * (kQBytes >> 4)) + (uint64_t)((k & 3) * 2);
-          // B: V rows 16k .. 16k+15 = two 1024-byte atoms per k-step
-          const uint64_t vd = vdesc + (uint64_t)(k * (2048 >> 4));
-          umma_bf16(tmem_o, pd, vd, idesc_o, k != 0);
-        }
-        tcgen05_commit(o_full);
-        tcgen05_commit(&kv_empty[vstage]);  // K(t), V(t) free once these MMAs retire
-      }
-    }
-    __syncwarp();
-  } else {
-    // ===== softmax: two threads per query row =====
-    const int quarter = warp & 3;                  // TMEM lanes this warp may touch
-    const int hf = (warp - 2) >> 2;                // 0: score cols 0..63 / dims 0..31, 1: cols 64..127 / dims 32..63
-    const int row = quarter * 32 + lane;           // row within the tile
-    const int qr = q0 + row;
-    const RowMask rm = make_row_mask(mask_mode, qr, L, S, seg1_start, c1);
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-    const uint32_t s_addr = tmem_s + lane_off + hf * 64;
-    const uint32_t o_addr = tmem_o + lane_off + hf * 32;
-    uint8_t *p_row = sP + hf * kQBytes + row * 128;
-    const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-    float acc[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-    float m = -CUDART_INF_F, l = 0.f;
-    for (int t = 0; t < n_tiles; ++t) {
-      const int j0 = t * BKV, jc0 = j0 + hf * 64;
-      if (lane == 0) mbar_wait(s_full, t & 1);   // one lane polls, the warp parks at the sync
-      __syncwarp();
-      tcgen05_fence_after();
-      // interior tile: every key of the tile is visible to the rows of this warp -> no per-element mask
-      // (warp-uniform: tcgen05.ld is .sync.aligned, a diverged warp must never reach it)
-      const bool interior = __all_sync(0xffffffffu, j0 + BKV <= rm.lim0);
-      float mx = interior ? half_row_max<false>(s_addr, rm, jc0) : half_row_max<true>(s_addr, rm, jc0);
-      // exchange the half-row maxima with the partner thread (same row, other column half)
-      if (hf == 1) xch[row] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      if (hf == 0) {
-        mx = fmaxf(mx, xch[row]);
-        xch[row] = mx;
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      if (hf == 1) mx = xch[row];
-      const float m_new = fmaxf(m, mx * sc);
-      const float m_use = m_new == -CUDART_INF_F ? 0.f : m_new;
-      const float corr = ex2(m - m_use);
-      // fold O_t of the previous tile (this also guarantees the previous P V has consumed the P buffer)
-      if (t > 0) {
-        if (lane == 0) mbar_wait(o_full, (t - 1) & 1);
-        __syncwarp();
-        tcgen05_fence_after();
-        uint32_t r[32];
-        tmem_ld32(o_addr, r);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty);
-      }
-      if (corr != 1.f) {  // rescale only when the running maximum moved
-#pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] *= corr;
-        l *= corr;
-      }
-      m = m_new;
-      l += interior ? half_row_p<false>(s_addr, rm, jc0, sc, m_use, p_row, row)
-                    : half_row_p<true>(s_addr, rm, jc0, sc, m_use, p_row, row);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P visible to the tensor-core proxy
-      tcgen05_fence_before();
-      // the partner must have read this thread's xch slot before the next tile overwrites it: the
-      // named barrier of the next iteration orders that (write -> bar -> read -> ... -> next write
-      // happens after the partner passed this iteration's read because both arrive at p_full first)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-    // last O_t
-    if (lane == 0) mbar_wait(o_full, (n_tiles - 1) & 1);
-    __syncwarp();
-    tcgen05_fence_after();
-    {
-      uint32_t r[32];
-      tmem_ld32(o_addr, r);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(r[i]);
-    }
-    // row sum = both halves
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // partner done with the max slot
-    if (hf == 1) xch[row] = l;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-    if (hf == 0) {
-      l += xch[row];
-      xch[row] = l;
-    }
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-    if (hf == 1) l = xch[row];
-    if (qr < L) {
-      const float inv = 1.f / l;
-      uint4 *dst = reinterpret_cast<uint4 *>(out + (int64_t)(r0 + qr) * d + h * HD + hf * 32);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        __nv_bfloat162 a0 = __floats2bfloat162_rn(acc[8 * j] * inv, acc[8 * j + 1] * inv);
-        __nv_bfloat162 a1 = __floats2bfloat162_rn(acc[8 * j + 2] * inv, acc[8 * j + 3] * inv);
-        __nv_bfloat162 a2 = __floats2bfloat162_rn(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv);
-        __nv_bfloat162 a3 = __floats2bfloat162_rn(acc[8 * j + 6] * inv, acc[8 * j + 7] * inv);
-        dst[j] = make_uint4(*reinterpret_cast<uint32_t *>(&a0), *reinterpret_cast<uint32_t *>(&a1),
-                            *reinterpret_cast<uint32_t *>(&a2), *reinterpret_cast<uint32_t *>(&a3));
-      }
-    }
-  }
-  __syncwarp();
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Ping-pong variant: the 128-key tile is split into two 64-key halves and EACH HALF HAS ITS OWN
+// Ping-pong pipeline: the 128-key tile is split into two 64-key halves and EACH HALF HAS ITS OWN
 // softmax group (4 warps, one thread per query row), its own score buffer S_g, its own P_g buffer
 // and its own output accumulator O_g in TMEM (columns: S_0 0..63, S_1 64..127, O_0 128..191,
 // O_1 192..255).  Group g runs an independent online softmax over keys {128 t + 64 g ...}; the two
@@ -663,19 +408,12 @@ int launch_attention_tcgen05(const bf16 *qkv, int64_t M, int B, int n_head, cons
   VB_TRY(tc::make_tmap(&tm, qkv, M, 3 * d, 3 * (int64_t)d, fa5::BQ));
   static bool attr = false;
   if (!attr) {
-    VB_CUDA(cudaFuncSetAttribute(fa5::attn_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa5::kSmemBytes));
     VB_CUDA(cudaFuncSetAttribute(fa5::attn_tcgen05_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa5::kSmemBytes));
     attr = true;
   }
-  static const bool paired = getenv("VB_ATTN_FA_PAIRED") != nullptr;  // previous variant: two threads per row
   dim3 grid((max_seqlen + fa5::BQ - 1) / fa5::BQ, n_head, B);
-  if (paired)
-    fa5::attn_tcgen05_kernel<<<grid, fa5::kThreads, fa5::kSmemBytes, s>>>(tm, n_head, cu_seqlens, text_lens, seg1_lens,
-                                                                        seg1_start, mask_mode, out, skip_partial);
-  else
-    fa5::attn_tcgen05_pp_kernel<<<grid, fa5::kThreads, fa5::kSmemBytes, s>>>(tm, n_head, cu_seqlens, text_lens,
-                                                                           seg1_lens, seg1_start, mask_mode, out,
-                                                                           skip_partial);
+  fa5::attn_tcgen05_pp_kernel<<<grid, fa5::kThreads, fa5::kSmemBytes, s>>>(tm, n_head, cu_seqlens, text_lens, seg1_lens,
+                                                                         seg1_start, mask_mode, out, skip_partial);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }

@@ -115,12 +115,6 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
                        int64_t cache_seq_stride, int cache_cap, const int32_t *text_len, const int32_t *prompt_len,
                        const int32_t *n_gen, float *out, void *out16, void *workspace, bool pdl, cudaStream_t s);
 
-// attention_decode_tma.cu (bf16 cache, TMA-staged K/V tiles)
-int launch_attn_decode_tma(const float *q, const float *qkv_part, int qkv_splits, int qkv_ldp, const float *qkv_bias,
-                           int B, int n_head, void *kcache, void *vcache, int64_t cache_seq_stride, int cache_cap,
-                           const int32_t *text_len, const int32_t *prompt_len, const int32_t *n_gen, float *out,
-                           void *out16, float *part_o, float *part_ml, int nsplit, bool pdl, cudaStream_t s);
-
 // decode_fused.cu
 int launch_relu_reduce(const float *partials, int splits, int ldp, const float *bias, int B, int N, bf16 *out16,
                        int64_t ldo, bool pdl, cudaStream_t s);
