@@ -331,6 +331,16 @@ def main():
     ar_bytes = ar_step_bytes(B, mean_len, esize)
     ar_step_s = (r["ar_ms"] / a.steps) / 1000.0 / max(1, r["steps"])
     ach = ar_bytes / ar_step_s / 1e9
+    # DRAM bytes of one decode step from the committed ncu capture (tools/ar_step_traffic.py), if there is one
+    traffic, traffic_src = None, None
+    tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "round1_ar_step_traffic.json")
+    if B == 64 and esize == 2 and os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic = tj["traffic_bytes"]
+        traffic_src = (f"profiles/round1_ar_step_traffic.json: ncu dram__bytes_read+write over the "
+                       f"{tj['kernels_in_step']} kernels of one step at context {tj['context_len']} "
+                       f"(algorithmic {tj['algorithmic_bytes']:.4g} B)")
     nar_fl = 7 * nar_pass_flops(B, S_TEXT + T_PROMPT + frames, frames)
     nar_s = (r["nar_ms"] / a.steps) / 1000.0
     line = {
@@ -348,7 +358,8 @@ def main():
                 "ms_per_step": re["ms"] / a.steps},
         "roofline": {"kernel": "AR decode step (CUDA graph of the per-layer LN+GEMV / KV-cache attention kernels)",
                      "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": ach / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                     "frac": ach / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": pk["source"],
                      "algorithmic_bytes_per_launch": ar_bytes, "launch_seconds": ar_step_s},
         "roofline_nar": {"kernel": "7 NAR passes (QKV/out/FFN GEMMs + attention + heads)", "bound": "tensor",
                          "achieved": nar_fl / nar_s / 1e12 if nar_s > 0 else None, "peak": pk["tflops"],

@@ -184,6 +184,9 @@ typedef struct vb_ar_head {
   int32_t greedy;             /* 1: argmax + stop rule + append on device; 0: logits only */
 } vb_ar_head;
 
+/* bytes of scratch for vb_ar_head_step / vb_ar_decode_step.  The buffer must be zero-filled once when it is
+ * allocated (it carries the two grid-barrier words of the persistent small-batch step, which the kernels
+ * themselves keep consistent from then on) and must not be shared between concurrently running streams. */
 size_t vb_ar_step_workspace(const vb_decoder_desc *desc, int B, int cache_cap);
 
 /* final LayerNorm + ar_predict_layer on rows h[B,d] (valle.py:1039), then (greedy) the stop

@@ -253,15 +253,17 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
     const bool pdl = use_pdl();
     // Tuning of the chain (measured on B200 at d=1024 / d_ff=4096 / B=64, profiles/round1_summary.md): split-K wide
     // enough to fill the SMs is not the optimum for the projections whose partial sums a reduce kernel has to add
-    // up again (FFN2: 9 splits beat 18, QKV: 5 beat 6); 40 % of the KV streams prefetched into L2 beat 20 / 60 %.
+    // up again (FFN2: 9 splits beat 18, QKV: 5 beat 6, FFN1: 2 beat 4); 40 % of the KV streams prefetched into L2
+    // beat 20 / 60 %.
     static const int pf_env = getenv("VB_KV_PREFETCH_PCT") ? atoi(getenv("VB_KV_PREFETCH_PCT")) : 40;
     const int pf_pct = B >= 16 ? pf_env : 0;
     static const int qkv_env = getenv("VB_SPLITS_QKV") ? atoi(getenv("VB_SPLITS_QKV")) : 0;
     static const int out_splits = getenv("VB_SPLITS_OUT") ? atoi(getenv("VB_SPLITS_OUT")) : 0;   // 0 = fill the SMs
-    static const int ffn1_splits = getenv("VB_SPLITS_FFN1") ? atoi(getenv("VB_SPLITS_FFN1")) : 0;
+    static const int ffn1_env = getenv("VB_SPLITS_FFN1") ? atoi(getenv("VB_SPLITS_FFN1")) : 0;
     static const int ffn2_env = getenv("VB_SPLITS_FFN2") ? atoi(getenv("VB_SPLITS_FFN2")) : 0;
     const int qkv_splits = qkv_env > 0 ? qkv_env : std::max(1, std::min(5, d / 128));
     const int ffn2_splits = ffn2_env > 0 ? ffn2_env : std::max(1, std::min(9, dff / 128));
+    const int ffn1_splits = ffn1_env > 0 ? ffn1_env : std::max(1, std::min(2, d / 128));
     float *P = (float *)w.gemm_ws;
     Pending pend;
     // the four projections of the chain each prefetch a quarter of the first pf_pct % of the KV streams that the
