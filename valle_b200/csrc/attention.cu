@@ -381,8 +381,9 @@ attn_decode_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *_
 }
 
 // bf16 two-phase kernel (scores of the whole chunk to shared memory, block softmax, then P.V) with the FIRST batch
-// of K rows fetched ahead of the q/k/v prologue and the first batch of V rows fetched ahead of the block softmax: all CTAs of the single wave run their phases in lock step, so
-// without this the HBM pipe idles through every prologue / softmax / epilogue of the launch.
+// of K rows fetched ahead of the q/k/v prologue (and, with the fused QKV prologue, ahead of the dependency wait)
+// and the first batch of V rows fetched ahead of the block softmax: all CTAs of the single wave run their phases
+// in lock step, so without this the HBM pipe idles through every prologue / softmax / epilogue of the launch.
 template <int U>
 __global__ void __launch_bounds__(128, 7)
 attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, bf16 *__restrict__ kcache,
