@@ -23,18 +23,21 @@ vp = C.c_void_p
 
 
 class LayerParams(C.Structure):
+    """vb_layer_params (include/valle_b200.h): device pointers of one TransformerEncoderLayer"""
     _fields_ = [(n, vp) for n in (
         "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
         "norm1_w", "norm1_b", "norm2_w", "norm2_b")]
 
 
 class DecoderDesc(C.Structure):
+    """vb_decoder_desc"""
     _fields_ = [("d_model", C.c_int32), ("n_head", C.c_int32), ("n_layer", C.c_int32),
                 ("d_ff", C.c_int32), ("wdtype", C.c_int32), ("layers", C.POINTER(LayerParams)),
                 ("final_norm_w", vp), ("final_norm_b", vp)]
 
 
 class ArState(C.Structure):
+    """vb_ar_state: device-resident state of the AR sampling loop (valle.py:1012-1057)"""
     _fields_ = [("B", C.c_int32), ("tok_stride", C.c_int32),
                 ("text_len", vp), ("prompt_len", vp), ("max_new", vp),
                 ("n_gen", vp), ("finished", vp), ("tokens", vp), ("x_cur", vp), ("logits", vp),
@@ -44,13 +47,14 @@ class ArState(C.Structure):
 
 
 class ArHead(C.Structure):
+    """vb_ar_head: ar_predict_layer + the embedding / position tables the sampler needs for the next row"""
     _fields_ = [("predict_w", vp), ("n_vocab", C.c_int32), ("eos_id", C.c_int32),
                 ("audio_emb", vp), ("alpha", vp), ("pe", vp),
                 ("pe_rows", C.c_int32), ("greedy", C.c_int32)]
 
 
 class VbError(RuntimeError):
-    pass
+    """a C-ABI call returned a non-zero status, or libvalle_b200.so is missing (there is no fallback path)"""
 
 
 _lib: Optional[C.CDLL] = None

@@ -33,6 +33,7 @@ NUM_AUDIO_TOKENS = 1024  # valle/models/macros.py:5
 
 @dataclass
 class EngineStats:
+    """CUDA-event timings (ms) of the phases of the last generate() call and the number of decode steps"""
     ar_steps: int = 0
     ar_ms: float = 0.0
     prefill_ms: float = 0.0
@@ -121,6 +122,10 @@ def _seg_ranges(starts, lens):
 
 
 class ValleEngine:
+    """Batched VALLE.inference / VALLE.continual (valle.py:961-1238) for B independent utterances: prefill of the
+    AR decoder with a KV cache, the AR sampling loop as one CUDA-graph replay per token with the stop rule on the
+    device (valle.py:1012-1057), then the 7 NAR passes (valle.py:1059-1137) over packed ragged rows.  Per utterance the
+    result is exactly what the reference's batch-1 call returns; everything below this class is the C ABI."""
     def __init__(self, model, dtype: torch.dtype = torch.float32, use_cuda_graph: bool = True):
         self.lib = L.load()
         self.model = model

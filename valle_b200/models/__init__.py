@@ -8,6 +8,7 @@ from .valle import VALLE, PromptedFeatures
 
 
 def str2bool(v):
+    """icefall.utils.str2bool as used by the reference's flag definitions"""
     if isinstance(v, bool):
         return v
     if str(v).lower() in ("yes", "true", "t", "y", "1"):
@@ -18,6 +19,7 @@ def str2bool(v):
 
 
 def add_model_arguments(parser: argparse.ArgumentParser):
+    """the reference's model flags with the same names and defaults (valle/models/__init__.py:18-95)"""
     a = parser.add_argument
     a("--model-name", type=str, default="VALL-E", help="VALL-E (VALL-F / Transformer are not built here).")
     a("--decoder-dim", type=int, default=1024, help="Embedding dimension in the decoder model.")
@@ -36,6 +38,7 @@ def add_model_arguments(parser: argparse.ArgumentParser):
 
 
 def get_model(params) -> nn.Module:
+    """valle/models/__init__.py:98-136 for model_name VALL-E: VALLE(decoder_dim, nhead, num_decoder_layers, ...)"""
     name = params.model_name.lower()
     if name not in ("vall-e", "valle"):
         raise NotImplementedError(

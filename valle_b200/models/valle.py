@@ -101,6 +101,7 @@ class VALLE(nn.Module):
 
     # ---- reference helper API (valle.py:294-333) --------------------------------------------
     def stage_parameters(self, stage: int = 1) -> Iterator[nn.Parameter]:
+        """parameters of training stage 1 (ar_*) or 2 (nar_*), valle.py:294-306"""
         assert stage > 0
         prefix = "ar_" if stage == 1 else "nar_"
         label = " AR" if stage == 1 else "NAR"
@@ -111,6 +112,7 @@ class VALLE(nn.Module):
                     yield param
 
     def stage_named_parameters(self, stage: int = 1) -> Iterator[Tuple[str, nn.Parameter]]:
+        """valle.py:308-320"""
         assert stage > 0
         prefix = "ar_" if stage == 1 else "nar_"
         if stage in (1, 2):
@@ -119,11 +121,13 @@ class VALLE(nn.Module):
                     yield pair
 
     def pad_y_eos(self, y, y_mask_int, eos_id):
+        """append EOS after the last valid frame and split into (input, target), valle.py:322-333"""
         targets = F.pad(y, (0, 1), value=0) + eos_id * F.pad(y_mask_int, (0, 1), value=1)
         return targets[:, :-1], targets[:, 1:]
 
     # ---- engine -------------------------------------------------------------------------------
     def engine(self, dtype: Optional[torch.dtype] = None):
+        """the batched decode engine bound to this model's parameters (one per storage dtype; `engine_dtype` default)"""
         from ..engine import ValleEngine
         dtype = dtype or self.engine_dtype
         e = self._engines.get(dtype)
@@ -191,5 +195,7 @@ class VALLE(nn.Module):
     def forward(self, x: torch.Tensor, x_lens: torch.Tensor, y: Union[torch.Tensor, PromptedFeatures],
                 y_lens: Union[torch.Tensor, PromptedFeatures], reduction: str = "sum", train_stage: int = 0,
                 **kwargs):
+        """VALLE.forward (valle.py:762-959), forward only: ((x, codes), loss, metrics) with the reference's loss value in
+        eval mode; raises in training mode (no backward pass is built) -> train_forward.valle_forward"""
         from ..train_forward import valle_forward
         return valle_forward(self, x, x_lens, y, y_lens, reduction=reduction, train_stage=train_stage, **kwargs)

@@ -26,6 +26,9 @@ class ValleARMask:
 
 
 class MultiheadAttention(nn.Module):
+    """valle/modules/activation.py:12-431 restricted to what VALLE instantiates (:72-197: packed `in_proj_weight`
+    [3d, d] + `in_proj_bias`, `out_proj` NonDynamicallyQuantizableLinear, xavier / zero init in the same order):
+    forward (:199-431) = F.multi_head_attention_forward (:408-427) -> vb_linear / vb_attention / vb_linear."""
     __constants__ = ["batch_first"]
 
     def __init__(self, embed_dim, num_heads, dropout=0.0, bias=True, add_bias_kv=False, add_zero_attn=False,

@@ -25,6 +25,8 @@ def build_sine_pe(n: int, dim_model: int) -> torch.Tensor:
 
 
 class TokenEmbedding(nn.Module):
+    """valle/modules/embedding.py:21-47: nn.Embedding under `word_embeddings` (same parameter name, so checkpoints
+    load unchanged), `weight` / `embedding(i)` accessors, forward = lookup (+ dropout, identity in eval) -> vb_embed_sum."""
     def __init__(self, dim_model: int, vocab_size: int, dropout: float = 0.0):
         super().__init__()
         self.vocab_size = vocab_size
@@ -50,6 +52,9 @@ class TokenEmbedding(nn.Module):
 
 
 class SinePositionalEmbedding(nn.Module):
+    """valle/modules/embedding.py:50-97: x * x_scale + alpha * pe[:, :T] with the sine table of :68-91 (built on the
+    CPU with the reference's own expression, kept as a plain attribute like :65, never in the checkpoint); `alpha`
+    is the only parameter.  forward -> vb_add_pe."""
     def __init__(self, dim_model: int, dropout: float = 0.0, scale: bool = False, alpha: bool = False):
         super().__init__()
         self.dim_model = dim_model

@@ -24,6 +24,8 @@ _shape_t = Union[int, List[int], torch.Size]
 
 
 class LayerNorm(nn.Module):
+    """valle/modules/transformer.py:17-80: LayerNorm whose forward also accepts (input, embedding) tuples and passes
+    the embedding through (:57-74); weight / bias parameters as in the reference.  forward -> vb_layernorm."""
     __constants__ = ["normalized_shape", "eps", "elementwise_affine"]
 
     def __init__(self, normalized_shape: _shape_t, eps: float = 1e-5, elementwise_affine: bool = True,
@@ -77,6 +79,10 @@ class AdaptiveLayerNorm(nn.Module):
 
 
 class TransformerEncoderLayer(nn.Module):
+    """valle/modules/transformer.py:178-334, pre-LN only (`norm_first=True`, the VALL-E configuration):
+    x += SA(norm1(x)); x += linear2(relu(linear1(norm2(x)))) (:297-302, _sa_block :315, _ff_block :332); optional
+    AdaptiveLayerNorm wrapping (:238-258).  Same sub-module and parameter names as the reference; a standalone
+    forward runs the one-layer native stack, a TransformerEncoder drives all layers through one vb_decoder_t."""
     __constants__ = ["batch_first", "norm_first"]
 
     def __init__(self, d_model: int, nhead: int, dim_feedforward: int = 2048, dropout: float = 0.1,
@@ -125,6 +131,8 @@ class TransformerEncoderLayer(nn.Module):
 
 
 class TransformerEncoder(nn.Module):
+    """valle/modules/transformer.py:337-406: N deep-copied layers (+ optional final norm).  forward (:363-406) over
+    padded [B, L, d] input maps to one vb_decoder_forward call on packed ragged rows (`NativeDecoder`)."""
     __constants__ = ["norm"]
 
     def __init__(self, encoder_layer, num_layers, norm=None):
@@ -136,6 +144,7 @@ class TransformerEncoder(nn.Module):
 
     # ---- native handle -----------------------------------------------------------------
     def native(self, dtype: torch.dtype = torch.float32) -> "NativeDecoder":
+        """the C-side handle of this stack for the given storage dtype (rebuilt when a parameter changed)"""
         nd = self._native.get(dtype)
         if nd is None or nd.stale():
             nd = NativeDecoder(self, dtype)

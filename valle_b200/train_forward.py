@@ -34,6 +34,9 @@ def _top10(logits: torch.Tensor, targets: torch.Tensor, ignore: int) -> torch.Te
 @torch.no_grad()
 def valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, reduction: str = "sum",
                   train_stage: int = 0, **kwargs):
+    """VALLE.forward of valle/models/valle.py:762-959 without the backward pass: AR stage (:807-877, causal mask
+    of :835-861 as VB_MASK_PADDED_AR), one random NAR stage (:879-941, prefix modes of _prepare_prompts :335-393),
+    cross-entropy with reduction `sum` (:877, :936-941) and the top-10 accuracies; returns ((x, codes), loss, metrics)."""
     from .models.valle import PromptedFeatures
     if model.training:
         raise NotImplementedError("valle_b200.VALLE.forward: forward-only (eval mode); the backward pass / "
