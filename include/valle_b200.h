@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 1
+#define VB_ABI_VERSION 2
 
 enum vb_status { VB_OK = 0, VB_ERR_ARG = 1, VB_ERR_CUDA = 2, VB_ERR_UNSUPPORTED = 3 };
 /* storage type of the big matrices / activations.  Accumulation is always fp32. */
@@ -41,7 +41,10 @@ enum vb_mask_mode {
      [seg1_start, seg1_start + seg1_lens[b]). */
   VB_MASK_PADDED_AR = 2, /* + text rows see text only, audio rows causal (the merged
                             attn_mask | key_padding_mask of valle.py:835-861) */
-  VB_MASK_PADDED = 3     /* key padding only (NAR training, valle.py:921-925) */
+  VB_MASK_PADDED = 3,    /* key padding only (NAR training, valle.py:921-925) */
+  VB_MASK_DENSE = 4      /* vb_attention only: an arbitrary boolean attn_mask [L, L] shared by all sequences and
+                            heads, non-zero byte = blocked (the tensor form of activation.py:199-431 `attn_mask`);
+                            exact-order CUDA-core kernel */
 };
 
 typedef void *vb_stream_t; /* cudaStream_t */
@@ -50,6 +53,10 @@ int vb_abi_version(void);
 const char *vb_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
 int64_t vb_launch_count(void);
+/* Profiling builds only (libvalle_b200_trace.so, compiled with -DVB_TRACE): bind a device ring
+ * buf[cap] / counter; the kernels of the AR decode step then append (globaltimer_ns << 8 | id) stamps
+ * (tools/trace_ar_step.py).  The product library returns VB_ERR_UNSUPPORTED. */
+int vb_trace_bind(unsigned long long *buf, unsigned int *counter, unsigned int cap);
 
 /* ------------------------------------------------------------------------------------------
  * a10  TokenEmbedding (valle/modules/embedding.py:21-47) and the 8-codebook sum composed by the
@@ -57,12 +64,16 @@ int64_t vb_launch_count(void);
  *   out[r,:] (=|+=) sum_{j<n_tables} tables[j][ tokens[r*tok_row_stride + j*tok_tab_stride] , :]
  *   summed in table order j = 0..n_tables-1 (same association order as the reference).
  *   tables: HOST array of n_tables device pointers to fp32 [vocab_j, d].
+ *   table_rows: NULL or HOST array of the n_tables vocabulary sizes.  nn.Embedding raises IndexError for
+ *   an id outside [0, vocab_j) (embedding.py:46); with table_rows given such an id is clamped (no
+ *   out-of-bounds read) and *err_flag (device int32, may be NULL) is OR-ed with 1 for the host to report.
  *   out_rows: NULL or device int32 [n_rows] destination row of each input row (ragged packing).
  *   accumulate = 0: out = sum ; 1: out += sum
  * ---------------------------------------------------------------------------------------- */
 int vb_embed_sum(const int64_t *tokens, int64_t tok_row_stride, int64_t tok_tab_stride,
-                 const float *const *tables, int n_tables, int64_t n_rows, int d, float *out,
-                 int64_t out_row_stride, const int32_t *out_rows, int accumulate, vb_stream_t stream);
+                 const float *const *tables, const int32_t *table_rows, int n_tables, int64_t n_rows, int d,
+                 float *out, int64_t out_row_stride, const int32_t *out_rows, int accumulate,
+                 int32_t *err_flag, vb_stream_t stream);
 
 /* a11  SinePositionalEmbedding.forward (embedding.py:93-97, scale=False):
  *   out[orow(r),:] = in[r,:] + alpha[0] * pe[pos(r), :], pos(r) = positions ? positions[r] : pos0 + r,
@@ -101,11 +112,13 @@ int vb_linear(const void *A, int a_dtype, int64_t lda, const void *W, int w_dtyp
  *   sequences.  qkv: [M, 3d] (Q|K|V column blocks, head h = columns [h*hd,(h+1)*hd) of each
  *   block), cu_seqlens: device int32 [B+1] row offsets, text_lens: device int32 [B] (only for
  *   VB_MASK_VALLE_AR).  out: [M, d].  If kcache != NULL the K and V rows are also written to
- *   the caches ([B, H, cache_cap, hd], dtype = dtype) at their sequence position. */
+ *   the caches ([B, H, cache_cap, hd], dtype = dtype) at their sequence position.
+ *   dense_mask: device uint8 [>= max_seqlen rows, dense_ld] for VB_MASK_DENSE (NULL otherwise). */
 int vb_attention(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
                  const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start,
                  int max_seqlen, int mask_mode, void *out, void *kcache, void *vcache,
-                 int64_t cache_seq_stride, int cache_cap, vb_stream_t stream);
+                 int64_t cache_seq_stride, int cache_cap, const uint8_t *dense_mask, int64_t dense_ld,
+                 vb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Decoder stack handle (transformer.py:337-406 TransformerEncoder of pre-LN
@@ -184,9 +197,8 @@ typedef struct vb_ar_head {
   int32_t greedy;             /* 1: argmax + stop rule + append on device; 0: logits only */
 } vb_ar_head;
 
-/* bytes of scratch for vb_ar_head_step / vb_ar_decode_step.  The buffer must be zero-filled once when it is
- * allocated (it carries the two grid-barrier words of the persistent small-batch step, which the kernels
- * themselves keep consistent from then on) and must not be shared between concurrently running streams. */
+/* bytes of scratch for vb_ar_head_step / vb_ar_decode_step.  The buffer must not be shared between
+ * concurrently running streams. */
 size_t vb_ar_step_workspace(const vb_decoder_desc *desc, int B, int cache_cap);
 
 /* final LayerNorm + ar_predict_layer on rows h[B,d] (valle.py:1039), then (greedy) the stop

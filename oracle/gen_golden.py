@@ -2,7 +2,7 @@
 (/root/reference, through oracle/ref_loader.py) on CPU in fp32.  Runs only in the build
 container; the fixtures travel to the GPU box, the reference does not.
 
-    python -m oracle.gen_golden [tiny] [batch] [config0] [big_short] [big_full]
+    python -m oracle.gen_golden [tiny] [batch] [config0] [big_short] [big_full] [topk]
 
 Every fixture stores: the model config, the weight seed (weights = the reference's default init
 under torch.manual_seed(seed); valle_b200.models.VALLE reproduces them bit-for-bit, checked by
@@ -182,6 +182,31 @@ def gen_big(ref, S, Tp, name):
     save(f"{name}.pt", rec)
 
 
+def gen_topk(ref):
+    """top-k / temperature sampling at a fixed torch seed (valle.py:1040-1043,1287-1302): the reference draws with
+    torch.multinomial from torch's CPU generator, once per generated token.  The engine reproduces the ids when it
+    samples on the host (engine.sample_on_host) from logits that agree to ~1e-5."""
+    d, h, l, pm, seed = 256, 4, 2, 1, 0
+    m = build_reference(ref, d, h, l, pm, seed)
+    g = torch.Generator().manual_seed(21)
+    x, y = make_inputs(g, 7, 18)
+    xl = torch.tensor([x.shape[1]], dtype=torch.int32)
+    cases = []
+    for top_k, temp, tseed in ((5, 0.9, 1234), (-100, 1.0, 7), (20, 1.3, 99)):
+        torch.manual_seed(tseed)
+        with torch.no_grad():
+            codes = m.inference(x, xl, y, None, top_k=top_k, temperature=temp)
+        sd = {k: v.detach() for k, v in m.state_dict().items()}
+        torch.manual_seed(tseed)
+        with torch.no_grad():
+            codes_o = O.inference(sd, O.OracleConfig(d, h, l, pm, 8), x, xl, y, None, top_k=top_k, temperature=temp)
+        assert torch.equal(codes, codes_o), "oracle restatement disagrees with the reference under sampling"
+        print(f"topk case top_k={top_k} T={temp} seed={tseed}: {codes.shape[1]} frames")
+        cases.append(dict(top_k=top_k, temperature=temp, torch_seed=tseed, codes=codes.to(torch.int16)))
+    save("tiny_topk.pt", dict(config=dict(d_model=d, nhead=h, num_layers=l, prefix_mode=pm, num_quantizers=8),
+                              weight_seed=seed, checksums=checksums(m.state_dict()), x=x, y=y, cases=cases))
+
+
 def main(argv):
     ref = load_reference()
     what = argv or ["tiny", "batch", "config0", "big_short"]
@@ -194,6 +219,8 @@ def main(argv):
         gen_config0(ref)
     if "big_short" in what:
         gen_big(ref, 6, 30, "big_short")
+    if "topk" in what:
+        gen_topk(ref)
     if "big_full" in what:
         gen_big(ref, 47, 225, "big_full")  # BASELINE.json configs[1]: 3 s prompt -> 753 frames
 

@@ -28,7 +28,8 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_abi_version_and_error_slot(lib):
-    assert lib.vb_abi_version() == 1
+    from valle_b200 import _lib
+    assert lib.vb_abi_version() == _lib.ABI_VERSION
     assert isinstance(lib.vb_last_error(), bytes)
     assert lib.vb_launch_count() >= 0
 
@@ -37,7 +38,7 @@ def test_argument_errors_are_reported_not_thrown(lib):
     from valle_b200 import _lib
     # n_tables out of range -> VB_ERR_ARG with a message, no CUDA call made
     arr = (ctypes.c_void_p * 1)(0)
-    st = lib.vb_embed_sum(0, 1, 0, arr, 9, 4, 256, 0, 256, 0, 0, 0)
+    st = lib.vb_embed_sum(0, 1, 0, arr, None, 9, 4, 256, 0, 256, 0, 0, 0, 0)
     assert st == 1
     assert b"n_tables" in lib.vb_last_error()
     with pytest.raises(_lib.VbError):

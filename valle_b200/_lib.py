@@ -12,9 +12,10 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvalle_b200.so")
 
+ABI_VERSION = 2
 VB_F32, VB_BF16 = 0, 1
 VB_EPI_NONE, VB_EPI_RELU, VB_EPI_RESIDUAL = 0, 1, 2
-VB_MASK_FULL, VB_MASK_VALLE_AR, VB_MASK_PADDED_AR, VB_MASK_PADDED = 0, 1, 2, 3
+VB_MASK_FULL, VB_MASK_VALLE_AR, VB_MASK_PADDED_AR, VB_MASK_PADDED, VB_MASK_DENSE = 0, 1, 2, 3, 4
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
@@ -65,15 +66,16 @@ PROTOTYPES = {
     "vb_abi_version": (C.c_int, []),
     "vb_last_error": (C.c_char_p, []),
     "vb_launch_count": (C.c_int64, []),
-    "vb_embed_sum": (C.c_int, [vp, C.c_int64, C.c_int64, C.POINTER(vp), C.c_int, C.c_int64, C.c_int, vp,
-                               C.c_int64, vp, C.c_int, vp]),
+    "vb_trace_bind": (C.c_int, [vp, vp, C.c_uint]),
+    "vb_embed_sum": (C.c_int, [vp, C.c_int64, C.c_int64, C.POINTER(vp), c_i32p, C.c_int, C.c_int64, C.c_int, vp,
+                               C.c_int64, vp, C.c_int, vp, vp]),
     "vb_add_pe": (C.c_int, [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, C.c_int, vp, C.c_int64, vp, vp]),
     "vb_layernorm": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, vp, vp, vp, C.c_float, vp, C.c_int, vp]),
     "vb_adaln_project": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "vb_linear": (C.c_int, [vp, C.c_int, C.c_int64, vp, C.c_int, vp, vp, C.c_int, C.c_int64, C.c_int64,
                             C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp]),
     "vb_attention": (C.c_int, [vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int,
-                               vp, vp, vp, C.c_int64, C.c_int, vp]),
+                               vp, vp, vp, C.c_int64, C.c_int, vp, C.c_int64, vp]),
     "vb_decoder_create": (C.c_int, [C.POINTER(DecoderDesc), C.POINTER(vp)]),
     "vb_decoder_destroy": (None, [vp]),
     "vb_decoder_forward_workspace": (C.c_size_t, [C.POINTER(DecoderDesc), C.c_int64]),
@@ -101,17 +103,18 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("VB_LIB_PATH", LIB_PATH)  # profiling builds: valle_b200/lib/libvalle_b200_trace.so
+    if not os.path.exists(path):
         raise VbError(
-            f"{LIB_PATH} is missing: the CUDA engine has not been built. Run "
+            f"{path} is missing: the CUDA engine has not been built. Run "
             "`python -m valle_b200.build` (or __graft_entry__.build()). There is no CPU/PyTorch fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.vb_abi_version() != 1:
-        raise VbError(f"ABI version mismatch: library {lib.vb_abi_version()} != binding 1")
+    if lib.vb_abi_version() != ABI_VERSION:
+        raise VbError(f"ABI version mismatch: library {lib.vb_abi_version()} != binding {ABI_VERSION}")
     _lib = lib
     return lib
 

@@ -23,6 +23,14 @@ void set_error(const char *fmt, ...) {
 }
 void count_launch() { __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED); }
 
+#ifdef VB_TRACE
+static trace_bind_fn g_trace_binders[32];
+static int g_n_trace_binders = 0;
+void trace_register(trace_bind_fn f) {
+  if (g_n_trace_binders < 32) g_trace_binders[g_n_trace_binders++] = f;
+}
+#endif
+
 }  // namespace vb
 
 using namespace vb;
@@ -35,6 +43,21 @@ struct vb_decoder {
 VB_API int vb_abi_version(void) { return VB_ABI_VERSION; }
 VB_API const char *vb_last_error(void) { return g_err; }
 VB_API int64_t vb_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+VB_API int vb_trace_bind(unsigned long long *buf, unsigned int *counter, unsigned int cap) {
+#ifdef VB_TRACE
+  for (int i = 0; i < g_n_trace_binders; ++i)
+    if (g_trace_binders[i](buf, counter, cap) != 0) {
+      set_error("vb_trace_bind: cudaMemcpyToSymbol failed");
+      return VB_ERR_CUDA;
+    }
+  return VB_OK;
+#else
+  (void)buf; (void)counter; (void)cap;
+  set_error("vb_trace_bind: not a profiling build (compile with -DVB_TRACE: python -m valle_b200.build --trace)");
+  return VB_ERR_UNSUPPORTED;
+#endif
+}
 
 VB_API int vb_linear(const void *A, int a_dtype, int64_t lda, const void *W, int w_dtype,
                          const float *bias, void *C, int c_dtype, int64_t ldc, int64_t M, int N, int K,
@@ -66,6 +89,11 @@ VB_API int vb_decoder_create(const vb_decoder_desc *desc, vb_decoder_t *out) {
   }
   d->desc = *desc;
   d->layers = new (std::nothrow) vb_layer_params[desc->n_layer];
+  if (!d->layers) {
+    delete d;
+    set_error("vb_decoder_create: out of host memory");
+    return VB_ERR_ARG;
+  }
   memcpy(d->layers, desc->layers, sizeof(vb_layer_params) * desc->n_layer);
   d->desc.layers = d->layers;
   *out = d;
@@ -118,7 +146,7 @@ VB_API int vb_decoder_forward(vb_decoder_t dec, float *x, int64_t M, int B, cons
     void *kc = kcache ? (char *)kcache + (size_t)l * cache_layer_stride * ts : nullptr;
     void *vc = vcache ? (char *)vcache + (size_t)l * cache_layer_stride * ts : nullptr;
     VB_TRY(launch_attention_varlen(qkv, dt, M, B, D.n_head, d / D.n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, max_seqlen,
-                                   mask_mode, att, kc, vc, cache_seq_stride, cache_cap, s));
+                                   mask_mode, att, kc, vc, cache_seq_stride, cache_cap, nullptr, 0, s));
     VB_TRY(vb_linear(att, dt, d, P.out_proj_w, dt, P.out_proj_b, x, VB_F32, d, M, d, d, VB_EPI_RESIDUAL,
                      nullptr, 0, stream));
     VB_TRY(vb_layernorm(x, d, nullptr, M, d, P.norm2_w, P.norm2_b, ada2, 1e-5f, xn, dt, stream));
@@ -140,8 +168,6 @@ struct StepWs {
   bf16 *xn16, *att16, *hb16;
   void *gemm_ws;
   size_t gemm_ws_bytes;
-  void *persist;   // scratch of the persistent small-batch step (decode_persistent.cu)
-  unsigned *sync;  // its two grid-barrier words (zero-initialised by the caller's workspace allocation)
   size_t total;
 };
 StepWs carve_step_ws(const vb_decoder_desc &D, int B, int cache_cap, void *base) {
@@ -160,10 +186,8 @@ StepWs carve_step_ws(const vb_decoder_desc &D, int B, int cache_cap, void *base)
   w.xn16 = (bf16 *)take((size_t)64 * d * 2);
   w.att16 = (bf16 *)take((size_t)64 * d * 2);
   w.hb16 = (bf16 *)take((size_t)64 * dff * 2);
-  w.gemm_ws_bytes = gemm_decode_workspace();
+  w.gemm_ws_bytes = gemm_decode_workspace((int)d, (int)dff);
   w.gemm_ws = take(w.gemm_ws_bytes);
-  w.persist = take(B <= 4 ? persistent_step_workspace(D, B) : 0);
-  w.sync = (unsigned *)take(256);
   w.total = (size_t)(p - (char *)base) + 256;
   return w;
 }
@@ -245,8 +269,6 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
   const size_t ts = elem_size(dt);
   StepWs w = carve_step_ws(D, B, st->cache_cap, workspace);
   float *x = st->x_cur;
-  if (head->greedy && persistent_step_supported(D, B, st->cache_cap))
-    return launch_persistent_step(D, dec->layers, head, st, w.persist, w.sync, s);
   if (use_tc_decode(D, B)) {
     // bf16 tensor-core path: LayerNorm(+pending residual) -> swap-AB split-K tcgen05 projections whose
     // partial sums are consumed by the next kernel in the chain (7 launches per layer, PDL-chained)
@@ -286,15 +308,16 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
                        pf_f2 = kv_slice(l + 1, 2);
       void *kc = (char *)st->kcache + (size_t)l * st->cache_layer_stride * ts;
       void *vc = (char *)st->vcache + (size_t)l * st->cache_layer_stride * ts;
-      QkvScatter sc{d, hd, w.q, kc, vc, st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen};
+      QkvScatter sc{d, hd, w.q, kc, vc, st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen,
+                    st->finished};
       VB_TRY(launch_ln_reduce(x, d, B, d, pend.part, pend.splits, pend.ldp, pend.bias, L.norm1_w, L.norm1_b, 1e-5f,
                               w.xn16, pdl, s));
       int s1 = 1, ldp1 = 0;
       VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.in_proj_w, 3 * d, d, qkv_splits, L.in_proj_b, DG_QKV, nullptr,
                                 nullptr, d, &sc, P, w.gemm_ws_bytes, &s1, &ldp1, &pf_qkv, pdl, s));
       VB_TRY(launch_attn_decode(w.q, s1 > 1 ? P : nullptr, s1, ldp1, L.in_proj_b, B, D.n_head, hd, kc, vc, dt,
-                                st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen, w.att,
-                                w.att16, w.attn_ws, pdl, s));
+                                st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen, st->finished,
+                                w.att, w.att16, w.attn_ws, pdl, s));
       int s2 = 1, ldp2 = 0;
       VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)L.out_proj_w, d, d, out_splits, L.out_proj_b, DG_RESIDUAL, x,
                                 nullptr, d, nullptr, P, w.gemm_ws_bytes, &s2, &ldp2, &pf_out, pdl, s));
@@ -318,11 +341,13 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
     const vb_layer_params &P = dec->layers[l];
     void *kc = (char *)st->kcache + (size_t)l * st->cache_layer_stride * ts;
     void *vc = (char *)st->vcache + (size_t)l * st->cache_layer_stride * ts;
-    QkvScatter sc{d, hd, w.q, kc, vc, st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen};
+    QkvScatter sc{d, hd, w.q, kc, vc, st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen,
+                    st->finished};
     LnParams ln1{P.norm1_w, P.norm1_b, nullptr, 1e-5f};
     VB_TRY(launch_gemv(x, d, B, P.in_proj_w, dt, P.in_proj_b, 3 * d, d, nullptr, 0, &ln1, 3, &sc, s));
     VB_TRY(launch_attn_decode(w.q, nullptr, 0, 0, nullptr, B, D.n_head, hd, kc, vc, dt, st->cache_seq_stride,
-                              st->cache_cap, st->text_len, st->prompt_len, st->n_gen, w.att, nullptr, w.attn_ws, false, s));
+                              st->cache_cap, st->text_len, st->prompt_len, st->n_gen, st->finished, w.att, nullptr,
+                              w.attn_ws, false, s));
     VB_TRY(launch_gemv(w.att, d, B, P.out_proj_w, dt, P.out_proj_b, d, d, x, d, nullptr, 2, nullptr, s));
     LnParams ln2{P.norm2_w, P.norm2_b, nullptr, 1e-5f};
     VB_TRY(launch_gemv(x, d, B, P.lin1_w, dt, P.lin1_b, dff, d, w.hb, dff, &ln2, 1, nullptr, s));

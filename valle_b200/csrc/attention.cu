@@ -26,7 +26,7 @@ attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__
                         const int32_t *__restrict__ text_lens, const int32_t *__restrict__ seg1_lens,
                         int seg1_start, int mask_mode, T *__restrict__ out,
                         T *__restrict__ kcache, T *__restrict__ vcache, int64_t cache_seq_stride,
-                        int cache_cap) {
+                        int cache_cap, const uint8_t *__restrict__ dmask, int64_t dld) {
   constexpr int LDT = 68;  // padded leading dim (floats), keeps float4 alignment
   extern __shared__ __align__(16) float smem[];
   float *Qt = smem;             // [64 e][LDT rows]
@@ -119,7 +119,9 @@ attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = j0 + tx * 4 + j;
-        s[i][j] = lim[i].ok(c) ? s[i][j] * 0.125f : -CUDART_INF_F;
+        bool seen = lim[i].ok(c);
+        if (dmask != nullptr && seen) seen = dmask[(int64_t)(q0 + ty * 4 + i) * dld + c] == 0;  // True = blocked
+        s[i][j] = seen ? s[i][j] * 0.125f : -CUDART_INF_F;
         mx = fmaxf(mx, s[i][j]);
       }
 #pragma unroll
@@ -173,8 +175,16 @@ attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__
 int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
                             const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,
                             int seg1_start, int max_seqlen, int mask_mode, void *out, void *kcache, void *vcache,
-                            int64_t cache_seq_stride, int cache_cap, cudaStream_t s) {
+                            int64_t cache_seq_stride, int cache_cap, const uint8_t *dense_mask, int64_t dense_ld,
+                            cudaStream_t s) {
   VB_CHECK_ARG(head_dim == HD, "attention: head_dim=%d, only 64 is built", head_dim);
+  VB_CHECK_ARG(mask_mode >= VB_MASK_FULL && mask_mode <= VB_MASK_DENSE, "attention: bad mask mode %d", mask_mode);
+  if (mask_mode == VB_MASK_DENSE) {
+    VB_CHECK_ARG(dense_mask != nullptr && dense_ld >= max_seqlen, "attention: VB_MASK_DENSE needs a [>=L, >=L] byte mask");
+    mask_mode = VB_MASK_FULL;  // every key of the sequence, minus the blocked entries of the dense mask
+  } else {
+    dense_mask = nullptr;
+  }
   VB_CHECK_ARG(mask_mode == VB_MASK_FULL || text_lens != nullptr, "attention: this mask mode needs text_lens");
   VB_CHECK_ARG(mask_mode < VB_MASK_PADDED_AR || seg1_lens != nullptr, "attention: padded mask modes need seg1_lens");
   if (M == 0 || B == 0) return VB_OK;
@@ -184,20 +194,21 @@ int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_
     auto k = attn_varlen_simt_kernel<float>;
     VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, 256, smem, s>>>((const float *)qkv, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, (float *)out,
-                              (float *)kcache, (float *)vcache, cache_seq_stride, cache_cap);
-  } else if (dtype == VB_BF16 && kcache == nullptr && getenv("VB_ATTN_SIMT") == nullptr && attention_tcgen05_enabled()) {
+                              (float *)kcache, (float *)vcache, cache_seq_stride, cache_cap, dense_mask, dense_ld);
+  } else if (dtype == VB_BF16 && dense_mask == nullptr && kcache == nullptr && getenv("VB_ATTN_SIMT") == nullptr &&
+             attention_tcgen05_enabled()) {
     // 128-row query tiles on tcgen05/TMEM; a ragged last tile is shifted back to [L-128, L) (overlap, rows are
     // independent) so that a length like 1025 costs 9 tiles, not 9 tiles plus a 64-row warp-level pass
     return launch_attention_tcgen05((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start,
                                     max_seqlen, mask_mode, (bf16 *)out, 2, s);
-  } else if (dtype == VB_BF16 && getenv("VB_ATTN_SIMT") == nullptr) {
+  } else if (dtype == VB_BF16 && dense_mask == nullptr && getenv("VB_ATTN_SIMT") == nullptr) {
     return launch_attention_mma((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, max_seqlen, mask_mode,
                                 (bf16 *)out, (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, 0, s);
   } else if (dtype == VB_BF16) {
     auto k = attn_varlen_simt_kernel<bf16>;
     VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, 256, smem, s>>>((const bf16 *)qkv, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, (bf16 *)out,
-                              (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap);
+                              (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, dense_mask, dense_ld);
   } else {
     set_error("attention: bad dtype %d", dtype);
     return VB_ERR_ARG;
@@ -235,6 +246,29 @@ struct QkvPartials {
   int splits, ldp;
 };
 
+// A finished utterance (stop rule fired, vb_ar_state.finished != 0) takes no further part in the step: its KV
+// cache stays as it is (nothing appended, nothing streamed) and its attention output row is zero.  Uniform
+// over the CTA.  Returns true if the CTA is done.
+__device__ __forceinline__ bool decode_row_finished(const int32_t *finished, int b, int h, int sp, int d, int tid,
+                                                    int nsplit, int n_head, float *out, bf16 *out16, float *part_o,
+                                                    float *part_ml) {
+  if (finished == nullptr || finished[b] == 0) return false;
+  if (tid < HD) {
+    if (nsplit == 1) {
+      out[(int64_t)b * d + h * HD + tid] = 0.f;
+      if (out16) out16[(int64_t)b * d + h * HD + tid] = __float2bfloat16_rn(0.f);
+    } else {
+      const int64_t pi = ((int64_t)b * n_head + h) * nsplit + sp;
+      part_o[pi * HD + tid] = 0.f;
+      if (tid == 0) {
+        part_ml[pi * 2] = -CUDART_INF_F;
+        part_ml[pi * 2 + 1] = 0.f;
+      }
+    }
+  }
+  return true;
+}
+
 // Single pass, no block-level synchronisation inside the loop: each 8-lane group owns every 16th key of
 // the chunk, streams the K row and the V row of its keys together (4 keys = 8 x 16-byte loads in
 // flight per lane), and keeps its OWN online-softmax state (m, l, 8 output elements per lane).  The 16
@@ -244,7 +278,8 @@ __global__ void __launch_bounds__(128)
 attn_decode_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *__restrict__ kcache,
                    T *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
                    const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
-                   const int32_t *__restrict__ n_gen, float *__restrict__ out, bf16 *__restrict__ out16,
+                   const int32_t *__restrict__ n_gen, const int32_t *__restrict__ finished,
+                   float *__restrict__ out, bf16 *__restrict__ out16,
                    float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit) {
   __shared__ __align__(16) float qs[HD];
   __shared__ __align__(16) float knew[HD];
@@ -256,6 +291,7 @@ attn_decode_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *_
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = n_head * HD;
   pdl_wait();
+  if (decode_row_finished(finished, b, h, sp, d, threadIdx.x, nsplit, n_head, out, out16, part_o, part_ml)) return;
   int kv_len = text_len[b] + prompt_len[b] + n_gen[b];
   kv_len = max(1, min(kv_len, cache_cap));
   const int pos = kv_len - 1;  // cache row of the current token
@@ -389,7 +425,8 @@ __global__ void __launch_bounds__(128, 7)
 attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, bf16 *__restrict__ kcache,
                    bf16 *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
                    const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
-                   const int32_t *__restrict__ n_gen, float *__restrict__ out, bf16 *__restrict__ out16,
+                   const int32_t *__restrict__ n_gen, const int32_t *__restrict__ finished,
+                   float *__restrict__ out, bf16 *__restrict__ out16,
                    float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit) {
   __shared__ float sc[kDecMaxChunk];
   __shared__ __align__(16) float qs[HD];
@@ -435,6 +472,8 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
     for (int j = 0; j < 3; ++j) qbias[j] = qp.bias[j * d + h * HD + tid];
   }
   pdl_wait();
+  vb_trace(TR_ATTN * 2);
+  if (decode_row_finished(finished, b, h, sp, d, tid, nsplit, n_head, out, out16, part_o, part_ml)) return;
   int n_gen_now;
   asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(n_gen_now) : "l"(n_gen + b) : "memory");
   if (n_gen_now != n_gen_early) setup(n_gen_now);  // uniform over the CTA
@@ -576,6 +615,7 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
       }
     }
   }
+  vb_trace(TR_ATTN * 2 + 1);
 }
 
 __global__ void attn_decode_combine_kernel(const float *__restrict__ part_o,
@@ -583,6 +623,7 @@ __global__ void attn_decode_combine_kernel(const float *__restrict__ part_o,
                                            float *__restrict__ out, bf16 *__restrict__ out16) {
   pdl_launch_dependents();
   pdl_wait();
+  vb_trace(TR_COMBINE * 2);
   const int h = blockIdx.x, b = blockIdx.y, e = threadIdx.x;
   const int64_t p0 = ((int64_t)b * n_head + h) * nsplit;
   float m = -CUDART_INF_F;
@@ -595,8 +636,9 @@ __global__ void attn_decode_combine_kernel(const float *__restrict__ part_o,
     l += part_ml[(p0 + s) * 2 + 1] * w;
     o += part_o[(p0 + s) * HD + e] * w;
   }
-  out[(int64_t)b * n_head * HD + h * HD + e] = o / l;
-  if (out16) out16[(int64_t)b * n_head * HD + h * HD + e] = __float2bfloat16_rn(o / l);
+  const float r = l > 0.f ? o / l : 0.f;  // l == 0: a finished utterance (every split empty)
+  out[(int64_t)b * n_head * HD + h * HD + e] = r;
+  if (out16) out16[(int64_t)b * n_head * HD + h * HD + e] = __float2bfloat16_rn(r);
 }
 
 static int decode_nsplit(int B, int n_head, int cache_cap) {
@@ -617,7 +659,8 @@ size_t attn_decode_workspace(int B, int n_head, int head_dim, int cache_cap) {
 int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, int qkv_ldp, const float *qkv_bias,
                        int B, int n_head, int head_dim, void *kcache, void *vcache, int dtype,
                        int64_t cache_seq_stride, int cache_cap, const int32_t *text_len, const int32_t *prompt_len,
-                       const int32_t *n_gen, float *out, void *out16, void *workspace, bool pdl, cudaStream_t s) {
+                       const int32_t *n_gen, const int32_t *finished, float *out, void *out16, void *workspace,
+                       bool pdl, cudaStream_t s) {
   VB_CHECK_ARG(head_dim == HD, "attn_decode: head_dim=%d, only 64 is built", head_dim);
   const int ns = decode_nsplit(B, n_head, cache_cap);
   VB_CHECK_ARG((cache_cap + ns - 1) / ns + 16 <= kDecMaxChunk, "attn_decode: cache_cap %d too large", cache_cap);
@@ -628,16 +671,16 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
   if (dtype == VB_F32 || getenv("VB_ATTN_DECODE_1PASS") != nullptr) {  // fp32 parity path / single-pass variant
     if (dtype == VB_F32)
       VB_CUDA(launch_kernel(attn_decode_kernel<float>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (float *)kcache,
-                            (float *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
+                            (float *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, finished, out,
                             (bf16 *)out16, part_o, part_ml, ns));
     else
       VB_CUDA(launch_kernel(attn_decode_kernel<bf16>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
-                            (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out,
+                            (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, finished, out,
                             (bf16 *)out16, part_o, part_ml, ns));
   } else {
     VB_CUDA(launch_kernel(attn_decode_2phase_pf_kernel<8>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
-                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, out, (bf16 *)out16,
-                          part_o, part_ml, ns));
+                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, finished, out,
+                          (bf16 *)out16, part_o, part_ml, ns));
   }
   count_launch();
   if (ns > 1) {
@@ -653,8 +696,9 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
 VB_API int vb_attention(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
                         const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start,
                         int max_seqlen, int mask_mode, void *out, void *kcache, void *vcache,
-                        int64_t cache_seq_stride, int cache_cap, vb_stream_t stream) {
+                        int64_t cache_seq_stride, int cache_cap, const uint8_t *dense_mask, int64_t dense_ld,
+                        vb_stream_t stream) {
   return vb::launch_attention_varlen(qkv, dtype, M, B, n_head, head_dim, cu_seqlens, text_lens, seg1_lens, seg1_start,
                                      max_seqlen, mask_mode, out, kcache, vcache, cache_seq_stride, cache_cap,
-                                     (cudaStream_t)stream);
+                                     dense_mask, dense_ld, (cudaStream_t)stream);
 }

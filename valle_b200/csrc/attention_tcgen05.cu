@@ -406,11 +406,9 @@ int launch_attention_tcgen05(const bf16 *qkv, int64_t M, int B, int n_head, cons
   const int d = n_head * fa5::HD;
   CUtensorMap tm;
   VB_TRY(tc::make_tmap(&tm, qkv, M, 3 * d, 3 * (int64_t)d, fa5::BQ));
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce once;
+  if (once.first())
     VB_CUDA(cudaFuncSetAttribute(fa5::attn_tcgen05_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa5::kSmemBytes));
-    attr = true;
-  }
   dim3 grid((max_seqlen + fa5::BQ - 1) / fa5::BQ, n_head, B);
   fa5::attn_tcgen05_pp_kernel<<<grid, fa5::kThreads, fa5::kSmemBytes, s>>>(tm, n_head, cu_seqlens, text_lens, seg1_lens,
                                                                          seg1_start, mask_mode, out, skip_partial);

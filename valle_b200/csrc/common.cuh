@@ -159,16 +159,67 @@ inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, 
   return launch_kernel_cluster(kern, grid, block, smem, s, pdl, dim3(1, 1, 1), args...);
 }
 
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs)
 inline int sm_count() {
-  static int n = 0;
-  if (n == 0) {
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = dev & 63;
+  if (n[slot] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[slot] = v > 0 ? v : 148;
+  }
+  return n[slot];
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per (function, device): remember which devices were done
+struct PerDeviceOnce {
+  bool done[64] = {false};
+  // true exactly once per device (callers then set their function attributes)
+  bool first() {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    const int slot = dev & 63;
+    if (done[slot]) return false;
+    done[slot] = true;
+    return true;
   }
-  return n;
+};
+
+// ---- device timeline (profiling builds only: -DVB_TRACE, libvalle_b200_trace.so) ----------------
+// Thread 0 of block (0,0,0) of a traced kernel appends (globaltimer << 8 | id) to a ring bound with
+// vb_trace_bind(); ids: kernel kind * 2 + (0 = dependency resolved, 1 = block 0 done).
+#ifdef VB_TRACE
+static __device__ unsigned long long *g_trace_buf = nullptr;
+static __device__ unsigned int *g_trace_cnt = nullptr;
+static __device__ unsigned int g_trace_cap = 0;
+__device__ __forceinline__ void vb_trace(int id) {
+  if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0 && g_trace_buf != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned i = atomicAdd(g_trace_cnt, 1u);
+    if (i < g_trace_cap) g_trace_buf[i] = (t << 8) | (unsigned long long)(id & 0xff);
+  }
 }
+typedef int (*trace_bind_fn)(unsigned long long *, unsigned int *, unsigned int);
+void trace_register(trace_bind_fn f);
+static int trace_bind_tu(unsigned long long *buf, unsigned int *cnt, unsigned int cap) {
+  if (cudaMemcpyToSymbol(g_trace_buf, &buf, sizeof(buf)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(g_trace_cnt, &cnt, sizeof(cnt)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)) != cudaSuccess) return 1;
+  return 0;
+}
+namespace {
+struct TraceReg {
+  TraceReg() { trace_register(trace_bind_tu); }
+};
+static TraceReg g_trace_reg;
+}  // namespace
+#else
+#define vb_trace(id) ((void)0)
+#endif
+enum { TR_LN = 1, TR_GEMM = 2, TR_ATTN = 3, TR_RELU = 4, TR_SAMPLE = 5, TR_COMBINE = 6, TR_FUSED = 7 };
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -31,6 +31,7 @@ ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *
     }
   }
   pdl_wait();
+  vb_trace(TR_LN * 2);
   float *xr = x + (int64_t)b * ldx;
   float4 v[kSlabs];
   float s = 0.f;
@@ -95,6 +96,7 @@ ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *
       *reinterpret_cast<uint2 *>(orow + c) = pk;
     }
   }
+  vb_trace(TR_LN * 2 + 1);
 }
 
 // out16[b, n] = bf16(relu(bias[n] + sum_s partials[s][b][n]))  -- FFN hidden activation
@@ -107,6 +109,7 @@ relu_reduce_kernel(const float *__restrict__ partials, int splits, int ldp, cons
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   const float4 bb = c < N ? *reinterpret_cast<const float4 *>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);  // ahead of the wait
   pdl_wait();
+  vb_trace(TR_RELU * 2);
   if (c >= N) return;
   const float *p = partials + (int64_t)b * ldp + c;
   float4 a = __ldcg(reinterpret_cast<const float4 *>(p));

@@ -10,21 +10,30 @@ namespace vb {
 static constexpr int kMaxTables = 8;
 struct TablePtrs {
   const float *t[kMaxTables];
+  int rows[kMaxTables];  // vocabulary size of each table, 0 = unknown (no check)
 };
 
 // out[r,:] (=|+=) sum_j tables[j][tok[r, j], :]   -- sum in order j = 0..n-1
 __global__ void embed_sum_kernel(const int64_t *__restrict__ tokens, int64_t tok_row_stride,
                                  int64_t tok_tab_stride, TablePtrs tabs, int n_tables, int64_t n_rows,
                                  int d, float *__restrict__ out, int64_t out_row_stride,
-                                 const int32_t *__restrict__ out_rows, int accumulate) {
+                                 const int32_t *__restrict__ out_rows, int accumulate,
+                                 int32_t *__restrict__ err_flag) {
   const int warps_per_block = blockDim.x >> 5;
   const int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   if (row >= n_rows) return;
   const int lane = threadIdx.x & 31;
   int64_t ids[kMaxTables];
 #pragma unroll
-  for (int j = 0; j < kMaxTables; ++j)
+  for (int j = 0; j < kMaxTables; ++j) {
     ids[j] = (j < n_tables) ? tokens[row * tok_row_stride + j * tok_tab_stride] : 0;
+    // nn.Embedding raises IndexError for an id outside the table (embedding.py:46); here the read is clamped
+    // (never out of bounds) and the caller's flag is raised so the host can report it
+    if (j < n_tables && tabs.rows[j] > 0 && (ids[j] < 0 || ids[j] >= tabs.rows[j])) {
+      if (err_flag != nullptr && lane == 0) atomicOr(err_flag, 1);
+      ids[j] = ids[j] < 0 ? 0 : tabs.rows[j] - 1;
+    }
+  }
   float *orow = out + (out_rows ? (int64_t)out_rows[row] : row) * out_row_stride;
   for (int c = lane * 4; c < d; c += 128) {
     float4 acc;
@@ -179,17 +188,21 @@ __global__ void gather_rows_kernel(const float *__restrict__ src, int64_t src_ro
 using namespace vb;
 
 VB_API int vb_embed_sum(const int64_t *tokens, int64_t tok_row_stride, int64_t tok_tab_stride,
-                            const float *const *tables, int n_tables, int64_t n_rows, int d,
-                            float *out, int64_t out_row_stride, const int32_t *out_rows, int accumulate,
-                            vb_stream_t stream) {
+                            const float *const *tables, const int32_t *table_rows, int n_tables,
+                            int64_t n_rows, int d, float *out, int64_t out_row_stride, const int32_t *out_rows,
+                            int accumulate, int32_t *err_flag, vb_stream_t stream) {
   VB_CHECK_ARG(n_tables >= 1 && n_tables <= kMaxTables, "vb_embed_sum: n_tables=%d not in [1,8]", n_tables);
   VB_CHECK_ARG(d % 4 == 0 && out_row_stride % 4 == 0, "vb_embed_sum: d and stride must be multiples of 4");
   if (n_rows == 0) return VB_OK;
   TablePtrs tp;
-  for (int j = 0; j < kMaxTables; ++j) tp.t[j] = j < n_tables ? tables[j] : nullptr;
+  for (int j = 0; j < kMaxTables; ++j) {
+    tp.t[j] = j < n_tables ? tables[j] : nullptr;
+    tp.rows[j] = (j < n_tables && table_rows) ? table_rows[j] : 0;
+  }
   const int wpb = 4;
   embed_sum_kernel<<<(unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-      tokens, tok_row_stride, tok_tab_stride, tp, n_tables, n_rows, d, out, out_row_stride, out_rows, accumulate);
+      tokens, tok_row_stride, tok_tab_stride, tp, n_tables, n_rows, d, out, out_row_stride, out_rows, accumulate,
+      err_flag);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }

@@ -294,11 +294,8 @@ VB_API int vb_conv1d(const float *x, int B, int Cin, int Tin, const float *w, co
   if (B == 0 || Tout <= 0) return VB_OK;
   const int in_w = (ec::T_T - 1) * stride + (K - 1) * dilation + 1;
   const size_t smem = (size_t)(ec::CO_T * ec::CI_T * ec::K_MAX + ec::CI_T * in_w) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    VB_CUDA(cudaFuncSetAttribute(ec::conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr = true;
-  }
+  static PerDeviceOnce once;
+  if (once.first()) VB_CUDA(cudaFuncSetAttribute(ec::conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   dim3 grid((Tout + ec::T_T - 1) / ec::T_T, (Cout + ec::CO_T - 1) / ec::CO_T, B);
   ec::conv1d_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, Cin, Tin, w, bias, Cout, K, stride, dilation, pad_left,
                                                               reflect, pre_elu, residual, out, Tout, in_w);

@@ -16,6 +16,8 @@
 //
 // Replaces F.linear at valle/modules/activation.py:408 (in/out-proj), valle/modules/transformer.py:332-334
 // (FFN) and valle/models/valle.py:1039 (ar_predict_layer) for the batched decode step.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tcgen05_ptx.cuh"
@@ -46,7 +48,7 @@ struct Epi {
   int d, head_dim, cache_cap;
   bf16 *kcache, *vcache;
   int64_t cache_seq_stride;
-  const int32_t *text_len, *prompt_len, *n_gen;
+  const int32_t *text_len, *prompt_len, *n_gen, *finished;
 };
 
 __device__ __forceinline__ void apply_epi(const Epi &e, int n, int b, float v) {
@@ -62,7 +64,7 @@ __device__ __forceinline__ void apply_epi(const Epi &e, int n, int b, float v) {
     const int part = n / e.d, c = n - part * e.d;
     if (part == 0) {
       e.out_f32[(int64_t)b * e.ld_out + c] = v;
-    } else {
+    } else if (e.finished == nullptr || e.finished[b] == 0) {
       const int h = c / e.head_dim, el = c - h * e.head_dim;
       int pos = e.text_len[b] + e.prompt_len[b] + e.n_gen[b] - 1;
       pos = max(0, min(pos, e.cache_cap - 1));
@@ -120,6 +122,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
         tma_load_2d(&tmap_w, &full_bar[i], tiles + i * kStageBytes, (kb0 + i) * BK, tile * TM);
       }
       pdl_wait();  // ... the activations do
+      vb_trace(TR_GEMM * 2);
       for (int i = 0; i < pre; ++i)
         tma_load_2d(&tmap_x, &full_bar[i], tiles + i * kStageBytes + kWBytes, (kb0 + i) * BK, 0);
       int stage = 0;
@@ -204,14 +207,19 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
   }
+  vb_trace(TR_GEMM * 2 + 1);
 }
 
 
 }  // namespace dg
 
-size_t gemm_decode_workspace() {
-  // fp32 partials [splits][64][ldp]: tiles * splits <= #SMs (or splits == 1), ldp = tiles * 128
-  return (size_t)(sm_count() + 32) * dg::TN * dg::TM * sizeof(float);
+size_t gemm_decode_workspace(int d_model, int d_ff) {
+  // fp32 partials [splits][64][ldp], ldp = tiles * 128: the automatic split count keeps tiles * splits <= #SMs;
+  // the forced / tuned counts of the decode chain (api.cu, VB_SPLITS_*) are capped at kMaxForcedSplits per
+  // projection, whose widest output is max(3 * d_model, d_ff) features
+  const size_t tiles_max = ((size_t)std::max(3 * d_model, d_ff) + dg::TM - 1) / dg::TM;
+  const size_t slabs = std::max((size_t)sm_count() + 32, tiles_max * kMaxForcedSplits);
+  return slabs * dg::TN * dg::TM * sizeof(float);
 }
 
 static int pick_splits(int tiles, int num_kb) {
@@ -228,7 +236,7 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
   VB_CHECK_ARG(K % tc::BK == 0 && ld_act % 8 == 0, "gemm_decode: K %% 64 != 0 or unaligned activations");
   const int tiles = (N + dg::TM - 1) / dg::TM;
   const int num_kb = K / tc::BK;
-  int splits = force_splits > 0 ? force_splits : pick_splits(tiles, num_kb);
+  int splits = force_splits > 0 ? std::min(force_splits, std::min(kMaxForcedSplits, num_kb)) : pick_splits(tiles, num_kb);
   const int ldp = tiles * dg::TM;
   if (splits > 1)
     VB_CHECK_ARG(partials && partial_bytes >= (size_t)splits * dg::TN * ldp * sizeof(float),
@@ -247,14 +255,13 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
     e.kcache = (bf16 *)qkv->kcache; e.vcache = (bf16 *)qkv->vcache;
     e.cache_seq_stride = qkv->cache_seq_stride;
     e.text_len = qkv->text_len; e.prompt_len = qkv->prompt_len; e.n_gen = qkv->n_gen;
+    e.finished = qkv->finished;
     e.out_f32 = qkv->q; e.ld_out = qkv->d;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first())
     VB_CUDA(cudaFuncSetAttribute(dg::gemm_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  dg::kSmemBytes));
-    attr_set = true;
-  }
   KvPrefetch pf0{};
   if (pf) pf0 = *pf;
   VB_CUDA(launch_kernel(dg::gemm_decode_kernel, dim3(tiles, splits), dim3(dg::kThreads), dg::kSmemBytes, s, pdl, tw,

@@ -151,7 +151,7 @@ struct GemvEpi {
   void *kcache, *vcache;
   int64_t cache_seq_stride;  // elements between sequences within one layer
   int cache_cap;
-  const int32_t *text_len, *prompt_len, *n_gen;
+  const int32_t *text_len, *prompt_len, *n_gen, *finished;
 };
 
 template <typename TW, int BT, int NPW>
@@ -257,7 +257,7 @@ gemv_kernel(const float *__restrict__ x, int64_t ldx, int B, const TW *__restric
               const int part = n / epi.d, c = n - part * epi.d;
               if (part == 0) {
                 epi.q[(int64_t)bb * epi.d + c] = v;
-              } else {
+              } else if (epi.finished == nullptr || epi.finished[bb] == 0) {
                 const int h = c / epi.head_dim, e = c - h * epi.head_dim;
                 int pos = epi.text_len[bb] + epi.prompt_len[bb] + epi.n_gen[bb] - 1;
                 pos = max(0, min(pos, epi.cache_cap - 1));
@@ -334,6 +334,7 @@ int launch_gemv(const float *x, int64_t ldx, int B, const void *W, int w_dtype, 
     epi.kcache = qkv->kcache; epi.vcache = qkv->vcache;
     epi.cache_seq_stride = qkv->cache_seq_stride; epi.cache_cap = qkv->cache_cap;
     epi.text_len = qkv->text_len; epi.prompt_len = qkv->prompt_len; epi.n_gen = qkv->n_gen;
+    epi.finished = qkv->finished;
   }
   const float *g = ln ? ln->gamma : nullptr, *bt = ln ? ln->beta : nullptr, *ada = ln ? ln->ada_wb : nullptr;
   const float eps = ln ? ln->eps : 0.f;

@@ -236,11 +236,8 @@ static int launch_t(const CUtensorMap &ta, const CUtensorMap &tb, const float *b
   VB_TRY(tc::make_tmap_2d(&tcm, C, M, N, ldc, BM, 128 / (int)sizeof(TC), sizeof(TC) == 4));
   using cfg = Cfg<BN>;
   auto kern = gemm_tcgen05_kernel<BN, kEpi, TC>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
-    attr_set = true;
-  }
+  static PerDeviceOnce once;  // per template instantiation and device
+  if (once.first()) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::kSmemBytes));
   const int tiles = ((M + BM - 1) / BM) * (N / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kern<<<grid, kThreads, cfg::kSmemBytes, s>>>(ta, tb, tcm, bias, M, N, K);

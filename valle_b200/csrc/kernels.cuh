@@ -66,6 +66,7 @@ struct QkvScatter {
   int64_t cache_seq_stride;
   int cache_cap;
   const int32_t *text_len, *prompt_len, *n_gen;
+  const int32_t *finished;  // NULL or [B]: rows that have stopped keep their cache untouched
 };
 
 // gemm_simt.cu
@@ -82,23 +83,19 @@ int launch_gemm_tcgen05(const bf16 *A, int64_t lda, const bf16 *W, const float *
 
 // gemm_decode.cu (swap-AB split-K tcgen05 projections for B <= 64 decode rows, bf16)
 enum { DG_F32 = 0, DG_RESIDUAL = 1, DG_RELU_BF16 = 2, DG_QKV = 3 };
-size_t gemm_decode_workspace();
+constexpr int kMaxForcedSplits = 16;  // cap of a caller-chosen split-K count (sizes the partial workspace)
+size_t gemm_decode_workspace(int d_model, int d_ff);
 int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, int N, int K, int force_splits,
                        const float *bias, int mode, float *out_f32, bf16 *out_bf16, int64_t ld_out,
                        const QkvScatter *qkv, float *partials, size_t partial_bytes, int *out_splits, int *out_ldp,
                        const KvPrefetch *pf, bool pdl, cudaStream_t s);
 
-// decode_persistent.cu (one cooperative kernel per AR decode step for 1..4 utterances, bf16)
-bool persistent_step_supported(const vb_decoder_desc &D, int B, int cache_cap);
-size_t persistent_step_workspace(const vb_decoder_desc &D, int B);
-int launch_persistent_step(const vb_decoder_desc &D, const vb_layer_params *layers, const vb_ar_head *head,
-                           vb_ar_state *st, void *scratch, unsigned *sync, cudaStream_t s);
-
 // attention.cu
 int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
                             const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,
                             int seg1_start, int max_seqlen, int mask_mode, void *out, void *kcache, void *vcache,
-                            int64_t cache_seq_stride, int cache_cap, cudaStream_t s);
+                            int64_t cache_seq_stride, int cache_cap, const uint8_t *dense_mask, int64_t dense_ld,
+                            cudaStream_t s);
 // attention_mma.cu (bf16 tensor-core flash attention)
 int launch_attention_mma(const bf16 *qkv, int64_t M, int B, int n_head, const int32_t *cu_seqlens,
                          const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
@@ -113,7 +110,8 @@ size_t attn_decode_workspace(int B, int n_head, int head_dim, int cache_cap);
 int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, int qkv_ldp, const float *qkv_bias,
                        int B, int n_head, int head_dim, void *kcache, void *vcache, int dtype,
                        int64_t cache_seq_stride, int cache_cap, const int32_t *text_len, const int32_t *prompt_len,
-                       const int32_t *n_gen, float *out, void *out16, void *workspace, bool pdl, cudaStream_t s);
+                       const int32_t *n_gen, const int32_t *finished, float *out, void *out16, void *workspace,
+                       bool pdl, cudaStream_t s);
 
 // decode_fused.cu
 int launch_relu_reduce(const float *partials, int splits, int ldp, const float *bias, int B, int N, bf16 *out16,

@@ -45,7 +45,15 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_launch_dependents();
   pdl_wait();
-  if (finished[b] != 0 && !reduce_only) return;  // uniform per CTA
+  vb_trace(TR_SAMPLE * 2);
+  if (finished[b] != 0 && !reduce_only) {  // uniform per CTA
+    // a stopped utterance still rides through the batched step: give it a fixed, bounded input row (its residual
+    // stream is updated in place by the layer chain and would otherwise drift step over step); the scatter and
+    // attention kernels skip its KV cache
+    float *xo = x_cur + (int64_t)b * d;
+    for (int c = tid * 4; c < d; c += 1024) *reinterpret_cast<float4 *>(xo + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   // scalars of the stop rule: in flight together with the logits instead of after the argmax
   const int n_new = n_gen[b], p_len = prompt_len[b], cap_new = max_new[b];
   const int forced_tok = forced ? (int)forced[b] : -1;
@@ -110,7 +118,11 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
   }
   __syncthreads();
   const int tok = s_tok;
-  if (tok < 0) return;
+  if (tok < 0) {  // stopped at this step: same fixed input row as above
+    float *xo = x_cur + (int64_t)b * d;
+    for (int c = tid * 4; c < d; c += 1024) *reinterpret_cast<float4 *>(xo + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   const float a = alpha[0];
   const float *e = audio_emb + (int64_t)tok * d;
   const float *p = pe + (int64_t)s_pos * d;

@@ -29,6 +29,29 @@ from . import _lib as L
 from . import ops
 
 NUM_AUDIO_TOKENS = 1024  # valle/models/macros.py:5
+NUM_TEXT_TOKENS = 512    # valle/models/macros.py:2
+
+
+def _on_device(fn):
+    """Run a method with the engine's GPU as the current CUDA device: every kernel launch, stream and event of the
+    call then belongs to `self.device` even when the caller's current device is another GPU of the box."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
+def _check_ids(tensors, hi: int, what: str):
+    """nn.Embedding raises IndexError for ids outside the table (valle/modules/embedding.py:46).  Host tensors are
+    checked here before the copy; device tensors are checked by the kernels (clamped read + flag, ops.check_oob)."""
+    for t in tensors:
+        if not t.is_cuda and t.numel() > 0:
+            lo_v, hi_v = int(t.min()), int(t.max())
+            if lo_v < 0 or hi_v >= hi:
+                raise IndexError(f"index out of range in self: {what} id {lo_v if lo_v < 0 else hi_v} not in [0, {hi})")
 
 
 @dataclass
@@ -141,6 +164,10 @@ class ValleEngine:
         self.prefix_mode = model.prefix_mode
         self.stats = EngineStats()
         self.quiet = False
+        #: top_k != 1 only: draw on the host exactly as the reference does (logits -> CPU, torch's CPU generator,
+        #: one utterance after the other), so that a fixed torch.manual_seed reproduces the reference's ids; the
+        #: default draws on the device (torch.multinomial on CUDA logits, Philox stream) without a per-token sync
+        self.sample_on_host = False
         #: micro-batches decoded concurrently on separate streams when B >= 32 (bf16 tensor-core path)
         self.micro_batches = 1
         self.replayed_launches = 0   # kernels executed through CUDA-graph replays
@@ -200,12 +227,19 @@ class ValleEngine:
 
     # ---- public API ----------------------------------------------------------------------
     @torch.no_grad()
+    @_on_device
     def generate(self, texts: Sequence[torch.Tensor], prompts: Sequence[torch.Tensor],
                  enroll_lens: Optional[Sequence[int]] = None, top_k: int = 1, temperature: float = 1.0,
                  max_new_tokens: Optional[int] = None, poll: int = 32,
-                 return_device: bool = False, trace: Optional[dict] = None) -> List[torch.Tensor]:
+                 return_device: bool = False, trace: Optional[dict] = None,
+                 forced: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
         """texts[b]: int64 [S_b] phoneme ids; prompts[b]: int64 [Tp_b, Q] codec ids (host or device).
-        Returns codes[b]: int64 [Tgen_b, Q] -- per utterance exactly what VALLE.inference returns."""
+        Returns codes[b]: int64 [Tgen_b, Q] -- per utterance exactly what VALLE.inference returns.
+
+        Test hooks: `trace` collects AR logits (trace["steps"] = set of iterations or "all") and, with
+        trace["nar"] = True, the NAR logits / argmax of every stage; `forced[b]` = int64 [T_b, Q] codes the decode is
+        teacher-forced with (every sampled id is replaced by the given one before it is appended, AR and NAR), so
+        that per-step logits can be compared with a reference that took exactly those ids."""
         self._refresh()
         m, dev, d, Q = self.model, self.device, self.d, self.Q
         B = len(texts)
@@ -213,12 +247,23 @@ class ValleEngine:
         S = [int(t.numel()) for t in texts]
         Tp = [int(p.shape[0]) for p in prompts]
         assert all(s > 0 for s in S) and all(p.shape[1] == Q for p in prompts)
+        _check_ids(texts, NUM_TEXT_TOKENS, "phoneme")
+        _check_ids([p[:, :1] for p in prompts], NUM_AUDIO_TOKENS + 1, "prompt code (first codebook)")  # 1025-row tables
+        _check_ids([p[:, 1:] for p in prompts], NUM_AUDIO_TOKENS, "prompt code")
         cap_new = [16 * s for s in S]  # valle.py:1047: stop when n_new > 16 * S
         if max_new_tokens is not None:
             cap_new = [min(c, max_new_tokens - 1) for c in cap_new]
         tok_stride = (max(cap_new) + 2 + 7) // 8 * 8
         cap = (max(S[b] + Tp[b] + cap_new[b] + 2 for b in range(B)) + 63) // 64 * 64
-        greedy = top_k == 1
+        greedy = top_k == 1 and forced is None
+        forced_steps = None
+        if forced is not None:  # [steps, B] first-codebook ids, EOS once an utterance's forced ids run out
+            n_f = max(int(f.shape[0]) for f in forced) + 1
+            forced_steps = torch.full((n_f + 1, B), NUM_AUDIO_TOKENS, dtype=torch.int64)
+            for b, f in enumerate(forced):
+                forced_steps[: f.shape[0], b] = f[:, 0].to(torch.int64).cpu()
+            forced_steps = forced_steps.to(dev)
+            cap_new = [min(c, int(f.shape[0])) for c, f in zip(cap_new, forced)]
 
         # ---- host -> device (once per batch) ----
         text_all = torch.cat([t.reshape(-1).to(torch.int64) for t in texts]).to(dev, non_blocking=True)
@@ -264,13 +309,20 @@ class ValleEngine:
         self._head_ref = head
         L.check(self.lib.vb_ar_head_step(self.ar.handle, C.byref(head), h_last.data_ptr(), C.byref(buf.st),
                                          buf.ws.data_ptr(), buf.ws.numel(), L.stream_ptr()), "vb_ar_head_step")
-        if not greedy:
-            self._sample_push(buf, head, top_k, temperature)
+        def want(step):
+            st_ = trace.get("steps", ())
+            return st_ == "all" or step in st_
         if trace is not None:  # test hook: AR logits of selected iterations (iteration 0 = prefill)
             trace.setdefault("ar_logits", {})
-            if 0 in trace.get("steps", ()):
+            if want(0):
                 trace["ar_logits"][0] = buf.logits[:, : self.n_vocab].clone()
             poll = 1
+        if forced_steps is not None:
+            poll = 1
+        if not greedy:
+            self._sample_push(buf, head, top_k, temperature, None if forced_steps is None else forced_steps[0])
+        if any(t.is_cuda for t in list(texts) + list(prompts)):
+            ops.check_oob(dev)  # ids that were already on the device are range-checked by the embedding kernels
         ev[1].record()
 
         # ---- AR decode loop (valle.py:1012-1057) ----
@@ -279,10 +331,13 @@ class ValleEngine:
         while steps < max_steps:
             n = min(poll, max_steps - steps)
             for _ in range(n):
-                self._decode_step(buf, head, greedy, top_k, temperature)
+                fs = None
+                if forced_steps is not None:
+                    fs = forced_steps[min(steps + 1, forced_steps.shape[0] - 1)]
+                self._decode_step(buf, head, greedy, top_k, temperature, fs)
             steps += n
             self._join_views(buf)
-            if trace is not None and steps in trace.get("steps", ()):
+            if trace is not None and want(steps):  # poll == 1 here: the logits row of iteration `steps`
                 trace["ar_logits"][steps] = buf.logits[:, : self.n_vocab].clone()
             if bool((buf.finished != 0).all()):  # one D2H sync per `poll` steps
                 break
@@ -306,9 +361,15 @@ class ValleEngine:
         src = torch.from_numpy(_seg_ranges(np.arange(B, dtype=np.int64) * tok_stride, Tg)[0]).to(dev)
         codes[:, 0] = buf.tokens.view(-1).index_select(0, src).to(torch.int64)
         if Q > 1:
-            self._nar(texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, enroll_lens)
+            fc = None
+            if forced is not None:
+                fc = torch.cat([forced[b][: Tg[b]].to(torch.int64) for b in range(B)]).to(dev)
+            self._nar(texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, enroll_lens, forced_codes=fc,
+                      trace=trace if (trace is not None and trace.get("nar")) else None)
         ev[3].record()
         ev[3].synchronize()
+        if any(t.is_cuda for t in list(texts) + list(prompts)):
+            ops.check_oob(dev)
         self.stats.prefill_ms = ev[0].elapsed_time(ev[1])
         self.stats.ar_ms = ev[1].elapsed_time(ev[2])
         self.stats.nar_ms = ev[2].elapsed_time(ev[3])
@@ -318,6 +379,7 @@ class ValleEngine:
         return [host[cu_g[b]:cu_g[b + 1]] for b in range(B)]
 
     @torch.no_grad()
+    @_on_device
     def continual(self, texts: Sequence[torch.Tensor], ys: Sequence[torch.Tensor]) -> List[torch.Tensor]:
         """VALLE.continual (valle.py:1139-1238): first-codebook codes are given, the 7 NAR stages
         predict the rest; prefix = min(T // 2, 225) frames."""
@@ -328,6 +390,9 @@ class ValleEngine:
         T = [int(y.shape[0]) for y in ys]
         Tp = [min(int(t * 0.5), 3 * 75) for t in T]
         Tg = [T[b] - Tp[b] for b in range(B)]
+        _check_ids(texts, NUM_TEXT_TOKENS, "phoneme")
+        _check_ids([y_[:, :1] for y_ in ys], NUM_AUDIO_TOKENS + 1, "code (first codebook)")
+        _check_ids([y_[:, 1:] for y_ in ys], NUM_AUDIO_TOKENS, "code")
         text_all = torch.cat([t.reshape(-1).to(torch.int64) for t in texts]).to(dev)
         prm_all = torch.cat([ys[b][:Tp[b]].to(torch.int64) for b in range(B)]).contiguous().to(dev)
         cu_g = [0]
@@ -336,6 +401,8 @@ class ValleEngine:
         codes = torch.empty((cu_g[-1], Q), dtype=torch.int64, device=dev)
         codes[:, 0] = torch.cat([ys[b][Tp[b]:, 0].to(torch.int64) for b in range(B)]).to(dev)
         self._nar(texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, None, trim_text=False)
+        if any(t.is_cuda for t in list(texts) + list(ys)):
+            ops.check_oob(dev)
         return [codes[cu_g[b]:cu_g[b + 1]] for b in range(B)]
 
     def kernel_launches(self) -> int:
@@ -379,7 +446,8 @@ class ValleEngine:
         for v in buf.views:
             main.wait_stream(v.stream)
 
-    def _decode_step(self, buf: _ArBuffers, head: L.ArHead, greedy: bool, top_k: int, temperature: float):
+    def _decode_step(self, buf: _ArBuffers, head: L.ArHead, greedy: bool, top_k: int, temperature: float,
+                     forced_step: Optional[torch.Tensor] = None):
         if self._use_views(buf, greedy):
             return self._decode_step_views(buf, head)
         if greedy and self.use_cuda_graph:
@@ -404,27 +472,34 @@ class ValleEngine:
             return
         self._launch_step(buf, head)
         if not greedy:
-            self._sample_push(buf, head, top_k, temperature)
+            self._sample_push(buf, head, top_k, temperature, forced_step)
 
     def _launch_step(self, buf, head: L.ArHead):
         L.check(self.lib.vb_ar_decode_step(self.ar.handle, C.byref(head), C.byref(buf.st), buf.ws.data_ptr(),
                                            buf.ws.numel(), L.stream_ptr()), "vb_ar_decode_step")
 
-    def _sample_push(self, buf: _ArBuffers, head: L.ArHead, top_k: int, temperature: float):
+    def _sample_push(self, buf: _ArBuffers, head: L.ArHead, top_k: int, temperature: float,
+                     forced_step: Optional[torch.Tensor] = None):
         """valle.py:1287-1302 topk_sampling with torch's own RNG stream (so a fixed torch seed gives
         the reference's draws), then the stop rule + append on the device."""
+        if forced_step is not None:  # teacher forcing (test hook): the given ids instead of a draw
+            samp = forced_step.contiguous()
+            L.check(self.lib.vb_ar_push_tokens(C.byref(head), C.byref(buf.st), samp.data_ptr(), self.d,
+                                               L.stream_ptr()), "vb_ar_push_tokens")
+            return
+        from .models.valle import topk_sampling
         logits = buf.logits[:, : self.n_vocab].clone()
-        if temperature != 1.0:
-            logits = logits / temperature
-        if top_k > 0:
-            k = min(max(top_k, 1), logits.size(-1))
-            kth = torch.topk(logits, k)[0][..., -1, None]
-            logits = logits.masked_fill(logits < kth, -float("inf"))
-        samp = torch.multinomial(torch.softmax(logits, dim=-1), num_samples=1).view(-1).contiguous()
+        if self.sample_on_host:
+            host = logits.cpu()
+            samp = torch.cat([topk_sampling(host[b:b + 1], top_k=top_k, top_p=1.0, temperature=temperature).view(-1)
+                              for b in range(host.shape[0])]).to(self.device)
+        else:
+            samp = topk_sampling(logits, top_k=top_k, top_p=1.0, temperature=temperature).view(-1).contiguous()
         L.check(self.lib.vb_ar_push_tokens(C.byref(head), C.byref(buf.st), samp.data_ptr(), self.d,
                                            L.stream_ptr()), "vb_ar_push_tokens")
 
-    def _nar(self, texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, enroll_lens, trim_text: bool = True):
+    def _nar(self, texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, enroll_lens, trim_text: bool = True,
+             forced_codes: Optional[torch.Tensor] = None, trace: Optional[dict] = None):
         m, dev, d, Q = self.model, self.device, self.d, self.Q
         B = len(S)
         pm = self.prefix_mode
@@ -498,8 +573,18 @@ class ValleEngine:
             hn = self.nar.final_norm(x, ada[i], rows=tgt_d, out_dtype=self.dtype)
             ops.linear(hn, self.nar_predict_w[i], None, L.VB_EPI_NONE, out=logits)
             nxt = emb[i + 1] if i < Q - 2 else None
-            # samples -> codes[:, i+1]; y_emb[generated rows] += emb[i+1][samples]  (valle.py:1130-1134)
-            ops.nar_argmax_accumulate(logits, codes[:, i + 1], codes.stride(0), nxt,
-                                      y_emb if nxt is not None else None, yg_d)
+            if trace is not None:
+                trace.setdefault("nar_logits", []).append(logits.clone())
+            if forced_codes is not None:  # teacher forcing (test hook): record the argmax, continue with the given ids
+                ops.nar_argmax_accumulate(logits, codes[:, i + 1], codes.stride(0), None, None, yg_d)
+                if trace is not None:
+                    trace.setdefault("nar_argmax", []).append(codes[:, i + 1].clone())
+                codes[:, i + 1] = forced_codes[:, i + 1]
+                if nxt is not None:
+                    ops.embed_sum(codes[:, i + 1:], Q, 0, [nxt], G, y_emb, out_rows=yg_d, accumulate=True)
+            else:
+                # samples -> codes[:, i+1]; y_emb[generated rows] += emb[i+1][samples]  (valle.py:1130-1134)
+                ops.nar_argmax_accumulate(logits, codes[:, i + 1], codes.stride(0), nxt,
+                                          y_emb if nxt is not None else None, yg_d)
             if pm == 0 and i < Q - 2:  # valle.py:1104-1107
                 ops.embed_sum(prm_all[:, i + 1:], Q, 0, [emb[i + 1]], sum(Tp), y_emb, out_rows=yp_d, accumulate=True)

@@ -17,6 +17,35 @@ from ..modules.transformer import AdaptiveLayerNorm, LayerNorm, TransformerEncod
 from .macros import NUM_AUDIO_TOKENS, NUM_TEXT_TOKENS
 
 
+def top_k_top_p_filtering(logits: torch.Tensor, top_k: int = 0, top_p: float = 1.0,
+                          filter_value: float = -float("Inf"), min_tokens_to_keep: int = 1) -> torch.Tensor:
+    """valle/models/valle.py:1242-1284: keep the k largest logits (`logits < kth -> filter_value`, so ties with the
+    k-th value survive, :1259) and / or the smallest nucleus whose probability mass reaches top_p; (batch, vocab)
+    logits on any device, modified in place like the reference."""
+    if top_k > 0:
+        k = min(max(top_k, min_tokens_to_keep), logits.size(-1))
+        kth = torch.topk(logits, k)[0][..., -1, None]
+        logits[logits < kth] = filter_value
+    if top_p < 1.0:
+        srt, order = torch.sort(logits, descending=True)
+        drop = torch.cumsum(F.softmax(srt, dim=-1), dim=-1) > top_p
+        if min_tokens_to_keep > 1:
+            drop[..., :min_tokens_to_keep] = 0
+        drop[..., 1:] = drop[..., :-1].clone()   # the first token above the threshold stays
+        drop[..., 0] = 0
+        logits[drop.scatter(1, order, drop)] = filter_value
+    return logits
+
+
+def topk_sampling(logits: torch.Tensor, top_k: int = 10, top_p: float = 1.0, temperature: float = 1.0) -> torch.Tensor:
+    """valle/models/valle.py:1287-1302: temperature, top-k / top-p filter, softmax, one torch.multinomial draw from
+    the default generator of the logits' device -- the same RNG consumption as the reference's call."""
+    if temperature != 1.0:
+        logits = logits / temperature
+    logits = top_k_top_p_filtering(logits, top_k=top_k, top_p=top_p)
+    return torch.multinomial(F.softmax(logits, dim=-1), num_samples=1)
+
+
 class PromptedFeatures:
     """valle/data/input_strategies.py:16-36 pair container accepted by forward() (prefix_mode 4)."""
 

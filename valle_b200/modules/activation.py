@@ -25,6 +25,53 @@ class ValleARMask:
         self.text_lens = text_lens
 
 
+def classify_attn_mask(attn_mask, L_q: int):
+    """Map the reference's `attn_mask` argument (activation.py:199-431) onto a kernel mask mode.
+
+    None -> (VB_MASK_FULL, None, None); ValleARMask -> (VB_MASK_VALLE_AR, text_lens, None); a boolean [L, L] tensor
+    (True = blocked, the form VALLE.inference builds at valle.py:1019-1033) is recognised as the VALL-E AR rule
+    `kv_len(i) = max(S, i + 1)` when it has exactly that shape -> (VB_MASK_VALLE_AR, S, None); an all-False mask ->
+    FULL; anything else -> (VB_MASK_DENSE, None, uint8 mask) served by the exact-order kernel."""
+    if attn_mask is None:
+        return L.VB_MASK_FULL, None, None
+    if isinstance(attn_mask, ValleARMask):
+        return L.VB_MASK_VALLE_AR, attn_mask.text_lens, None
+    if not isinstance(attn_mask, Tensor) or attn_mask.dim() != 2 or attn_mask.shape != (L_q, L_q):
+        raise NotImplementedError("valle_b200: attn_mask must be None, a ValleARMask or a boolean [L, L] tensor")
+    if attn_mask.dtype != torch.bool:
+        if attn_mask.is_floating_point():  # additive float mask: -inf = blocked (valle.py:852-861 builds these)
+            if not bool(((attn_mask == 0) | (attn_mask == float("-inf"))).all()):
+                raise NotImplementedError("valle_b200: float attn_mask must hold only 0 / -inf")
+            attn_mask = attn_mask == float("-inf")
+        else:
+            attn_mask = attn_mask != 0
+    if not bool(attn_mask.any()):
+        return L.VB_MASK_FULL, None, None
+    S = int((~attn_mask[0]).sum())
+    rows = torch.arange(L_q, device=attn_mask.device)
+    expect = rows[None, :] >= torch.clamp(rows + 1, min=S)[:, None]
+    if torch.equal(attn_mask, expect):
+        return L.VB_MASK_VALLE_AR, S, None
+    return L.VB_MASK_DENSE, None, attn_mask.to(torch.uint8).contiguous()
+
+
+def pack_rows(B: int, Lq: int, key_padding_mask: Optional[Tensor], device):
+    """(row index of every valid position in the flattened [B*L] layout, cu_seqlens, lens) for a suffix-padding
+    `key_padding_mask` (True = padding; make_pad_mask's form, valle.py:804-805)."""
+    lens = torch.full((B,), Lq, dtype=torch.int32)
+    if key_padding_mask is not None:
+        kpm = key_padding_mask.to(torch.bool)
+        lens = (~kpm).sum(dim=1).to(torch.int32).cpu()
+        # suffix padding only: valid positions must be a prefix of every row
+        pos = torch.arange(Lq, device=kpm.device)[None, :]
+        if not torch.equal(kpm, pos >= lens.to(kpm.device)[:, None]):
+            raise NotImplementedError("valle_b200: key_padding_mask must mark a padded suffix of every sequence")
+    idx = torch.cat([torch.arange(int(n)) + b * Lq for b, n in enumerate(lens)]).to(device)
+    cu = torch.zeros(B + 1, dtype=torch.int32)
+    cu[1:] = torch.cumsum(lens, 0)
+    return idx, cu.to(device), lens
+
+
 class MultiheadAttention(nn.Module):
     """valle/modules/activation.py:12-431 restricted to what VALLE instantiates (:72-197: packed `in_proj_weight`
     [3d, d] + `in_proj_bias`, `out_proj` NonDynamicallyQuantizableLinear, xavier / zero init in the same order):
@@ -68,25 +115,21 @@ class MultiheadAttention(nn.Module):
         if not self.batch_first or need_weights:
             raise NotImplementedError("valle_b200.MultiheadAttention: batch_first=True, need_weights=False only")
         B, Lq, d = query.shape
-        x = query.reshape(B * Lq, d).contiguous()
-        lens = torch.full((B,), Lq, dtype=torch.int32)
-        if key_padding_mask is not None:
-            lens = (~key_padding_mask).sum(dim=1).to(torch.int32).cpu()
-        # pack valid rows of every sequence
-        idx = torch.cat([torch.arange(int(n)) + b * Lq for b, n in enumerate(lens)]).to(x.device)
-        xp = x.index_select(0, idx)
-        cu = torch.zeros(B + 1, dtype=torch.int32)
-        cu[1:] = torch.cumsum(lens, 0)
-        cu = cu.to(x.device)
-        mode, tl = L.VB_MASK_FULL, None
-        if isinstance(attn_mask, ValleARMask):
-            mode, tl = L.VB_MASK_VALLE_AR, attn_mask.text_lens.to(device=x.device, dtype=torch.int32)
-        elif attn_mask is not None:
-            raise NotImplementedError("valle_b200.MultiheadAttention: pass attn_mask=ValleARMask(text_lens) "
-                                      "(structured form of valle.py:1010-1033) or None")
-        qkv = ops.linear(xp, self.in_proj_weight.detach(), self.in_proj_bias.detach())
-        o = ops.attention(qkv, cu, int(lens.max()), self.num_heads, mode, tl)
+        x = query.reshape(B * Lq, d).to(torch.float32).contiguous()
+        idx, cu, lens = pack_rows(B, Lq, key_padding_mask, x.device)
+        xp = x.index_select(0, idx)   # pack valid rows of every sequence
+        mode, tl, dense = classify_attn_mask(attn_mask, Lq)
+        o = self.attend_packed(xp, cu, int(lens.max()), B, mode, tl, dense)
         o = ops.linear(o, self.out_proj.weight.detach(), self.out_proj.bias.detach())
         out = torch.zeros_like(x)
         out.index_copy_(0, idx, o)
         return out.view(B, Lq, d), None
+
+    def attend_packed(self, xp: Tensor, cu: Tensor, max_len: int, B: int, mode: int, tl, dense) -> Tensor:
+        """in-proj + scaled-dot-product attention over packed rows (before out_proj)"""
+        if mode == L.VB_MASK_VALLE_AR:
+            if isinstance(tl, int):
+                tl = torch.full((B,), tl, dtype=torch.int32)
+            tl = tl.to(device=xp.device, dtype=torch.int32)
+        qkv = ops.linear(xp, self.in_proj_weight.detach(), self.in_proj_bias.detach())
+        return ops.attention(qkv, cu, max_len, self.num_heads, mode, tl, dense_mask=dense)

@@ -18,7 +18,7 @@ from torch.nn import functional as F
 
 from .. import _lib as L
 from .. import ops
-from .activation import MultiheadAttention, ValleARMask
+from .activation import MultiheadAttention, ValleARMask, classify_attn_mask, pack_rows
 
 _shape_t = Union[int, List[int], torch.Size]
 
@@ -119,6 +119,21 @@ class TransformerEncoderLayer(nn.Module):
             self.norm1 = norm1
             self.norm2 = norm2
 
+    def forward_packed(self, xp: Tensor, cu: Tensor, max_len: int, B: int, mode: int, tl, dense,
+                       ada1: Optional[Tensor], ada2: Optional[Tensor]) -> Tensor:
+        """transformer.py:296-302 on packed rows xp [M, d] fp32, in place, operator by operator:
+        x += out_proj(SA(norm1(x))); x += linear2(relu(linear1(norm2(x))))."""
+        n1 = self.norm1.norm if isinstance(self.norm1, AdaptiveLayerNorm) else self.norm1
+        n2 = self.norm2.norm if isinstance(self.norm2, AdaptiveLayerNorm) else self.norm2
+        h = ops.layernorm(xp, n1.weight.detach(), n1.bias.detach(), n1.eps, ada1)
+        o = self.self_attn.attend_packed(h, cu, max_len, B, mode, tl, dense)
+        ops.linear(o, self.self_attn.out_proj.weight.detach(), self.self_attn.out_proj.bias.detach(),
+                   epilogue=L.VB_EPI_RESIDUAL, out=xp)
+        h = ops.layernorm(xp, n2.weight.detach(), n2.bias.detach(), n2.eps, ada2)
+        f = ops.linear(h, self.linear1.weight.detach(), self.linear1.bias.detach(), epilogue=L.VB_EPI_RELU)
+        ops.linear(f, self.linear2.weight.detach(), self.linear2.bias.detach(), epilogue=L.VB_EPI_RESIDUAL, out=xp)
+        return xp
+
     def forward(self, src, src_mask=None, src_key_padding_mask: Optional[Tensor] = None):
         """One pre-LN layer (transformer.py:296-302) -- runs a 1-layer native stack."""
         enc = TransformerEncoder.__new__(TransformerEncoder)
@@ -127,6 +142,7 @@ class TransformerEncoderLayer(nn.Module):
         enc.num_layers = 1
         enc.norm = None
         enc._native = {}
+        enc.training = self.training
         return enc.forward(src, mask=src_mask, src_key_padding_mask=src_key_padding_mask)
 
 
@@ -166,40 +182,55 @@ class TransformerEncoder(nn.Module):
 
     def forward(self, src, mask=None, src_key_padding_mask: Optional[Tensor] = None,
                 return_layer_states: bool = False):
-        """transformer.py:363-406.  `src` is `x` or `(x, stage_embedding)`; `mask` is None or a
-        ValleARMask; `src_key_padding_mask` a bool [B, L] suffix-padding mask."""
-        if return_layer_states:
-            raise NotImplementedError("valle_b200.TransformerEncoder: return_layer_states is not built")
+        """transformer.py:363-406.  `src` is `x` or `(x, stage_embedding)`; `mask` is None, a ValleARMask or the
+        reference's boolean [L, L] `attn_mask` tensor (True = blocked; the VALL-E AR pattern of valle.py:1019-1033
+        is recognised and served by the structured kernels, any other pattern by the dense-mask kernel);
+        `src_key_padding_mask` a bool [B, L] suffix-padding mask.  `return_layer_states=True` returns
+        (layer_states, output) as transformer.py:368-381 does."""
         if not self.layers[0].norm_first:
             raise NotImplementedError("valle_b200: post-LN (norm_first=False) is not on the VALL-E hot path")
-        if self.training:
-            raise NotImplementedError("valle_b200: call .eval() -- training-mode dropout is not built")
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("valle_b200.TransformerEncoder: the module-level forward is inference only "
+                                      "(training goes through VALLE.forward); call .eval()")
         is_tuple = isinstance(src, tuple)
         x, stage = src if is_tuple else (src, None)
         B, Lq, d = x.shape
         dev = x.device
-        lens = torch.full((B,), Lq, dtype=torch.int32)
-        if src_key_padding_mask is not None:
-            lens = (~src_key_padding_mask).sum(dim=1).to(torch.int32).cpu()
-        idx = torch.cat([torch.arange(int(n)) + b * Lq for b, n in enumerate(lens)]).to(dev)
-        xp = x.reshape(B * Lq, d).to(torch.float32).index_select(0, idx).contiguous()
-        cu = torch.zeros(B + 1, dtype=torch.int32)
-        cu[1:] = torch.cumsum(lens, 0)
-        cu = cu.to(dev)
-        mode, tl = L.VB_MASK_FULL, None
-        if isinstance(mask, ValleARMask):
-            mode, tl = L.VB_MASK_VALLE_AR, mask.text_lens.to(device=dev, dtype=torch.int32)
-        elif mask is not None:
-            raise NotImplementedError("valle_b200.TransformerEncoder: pass mask=ValleARMask(text_lens) or None")
-        nd = self.native(torch.float32)
-        ada = nd.ada_table(stage) if stage is not None else None
-        nd.forward(xp, cu, B, int(lens.max()), mode, tl, ada)
-        if self.norm is not None:
-            xp = nd.final_norm(xp, ada)
-        out = torch.zeros((B * Lq, d), dtype=torch.float32, device=dev)
-        out.index_copy_(0, idx, xp)
-        out = out.view(B, Lq, d)
-        return (out, stage) if is_tuple else out
+        with torch.cuda.device(dev):
+            idx, cu, lens = pack_rows(B, Lq, src_key_padding_mask, dev)
+            xp = x.reshape(B * Lq, d).to(torch.float32).index_select(0, idx).contiguous()
+            mode, tl, dense = classify_attn_mask(mask, Lq)
+            max_len = int(lens.max())
+
+            def unpack(t):
+                out = torch.zeros((B * Lq, d), dtype=torch.float32, device=dev)
+                out.index_copy_(0, idx, t)
+                return out.view(B, Lq, d)
+
+            nd = self.native(torch.float32)
+            ada = nd.ada_table(stage) if stage is not None else None
+            if mode != L.VB_MASK_DENSE and not return_layer_states:
+                if mode == L.VB_MASK_VALLE_AR:
+                    tl = (torch.full((B,), tl, dtype=torch.int32) if isinstance(tl, int) else tl).to(
+                        device=dev, dtype=torch.int32)
+                nd.forward(xp, cu, B, max_len, mode, tl, ada)   # the whole stack in one C call
+                if self.norm is not None:
+                    xp = nd.final_norm(xp, ada)
+                out = unpack(xp)
+                return (out, stage) if is_tuple else out
+            # layer by layer through the operator surface (dense masks, per-layer states)
+            states = []
+            for i, lyr in enumerate(self.layers):
+                lyr.forward_packed(xp, cu, max_len, B, mode, tl, dense,
+                                   None if ada is None else ada[2 * i], None if ada is None else ada[2 * i + 1])
+                if return_layer_states:
+                    states.append(unpack(xp))
+            if self.norm is not None:
+                xp = nd.final_norm(xp, ada)
+            out = unpack(xp)
+            if return_layer_states:
+                return states, ((out, stage) if is_tuple else out)
+            return (out, stage) if is_tuple else out
 
 
 class NativeDecoder:

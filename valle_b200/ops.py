@@ -25,25 +25,71 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _dev_guard(fn):
+    """Launch on the GPU the tensors live on: the first CUDA tensor argument's device becomes the current device for
+    the call, so the stream, the per-device function attributes and the SM count all belong to that GPU even when
+    the caller's current device is another one."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index == torch.cuda.current_device():
+                    break
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def table_array(tables: Sequence[torch.Tensor]):
     arr = (C.c_void_p * len(tables))(*[t.data_ptr() for t in tables])
     return arr
 
 
+_OOB: dict = {}
+
+
+def oob_flag(device) -> torch.Tensor:
+    """per-device int32 flag the embedding kernels raise when a token id is outside its table"""
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    f = _OOB.get(key)
+    if f is None:
+        f = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", key))
+        _OOB[key] = f
+    return f
+
+
+def check_oob(device) -> None:
+    """nn.Embedding's contract (valle/modules/embedding.py:46): an id outside the table is an IndexError.
+    The kernels clamp the read and raise the device flag; this reads it (one D2H sync) and reports."""
+    f = oob_flag(device)
+    if int(f.item()) != 0:
+        f.zero_()
+        raise IndexError("index out of range in self (token id outside its embedding table)")
+
+
+@_dev_guard
 def embed_sum(tokens: torch.Tensor, tok_row_stride: int, tok_tab_stride: int,
               tables: Sequence[torch.Tensor], n_rows: int, out: torch.Tensor,
               out_rows: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
-    """out[orow(r)] (=|+=) sum_j tables[j][tokens[r*row_stride + j*tab_stride]]  (valle.py:1064,1110-1113)."""
+    """out[orow(r)] (=|+=) sum_j tables[j][tokens[r*row_stride + j*tab_stride]]  (valle.py:1064,1110-1113).
+    Ids outside a table are clamped and flagged (see check_oob)."""
     _req_cuda(tokens, out, *tables)
     assert tokens.dtype == torch.int64 and out.dtype == torch.float32
     d = out.shape[-1]
     lib = L.load()
-    L.check(lib.vb_embed_sum(tokens.data_ptr(), tok_row_stride, tok_tab_stride, table_array(tables),
+    rows = (C.c_int32 * len(tables))(*[int(t.shape[0]) for t in tables])
+    L.check(lib.vb_embed_sum(tokens.data_ptr(), tok_row_stride, tok_tab_stride, table_array(tables), rows,
                              len(tables), n_rows, d, out.data_ptr(), out.stride(-2) if out.dim() > 1 else d,
-                             L.ptr(out_rows), int(accumulate), _stream()), "vb_embed_sum")
+                             L.ptr(out_rows), int(accumulate), oob_flag(out.device).data_ptr(), _stream()),
+            "vb_embed_sum")
     return out
 
 
+@_dev_guard
 def add_pe(inp: torch.Tensor, pe: torch.Tensor, alpha: torch.Tensor, out: torch.Tensor, n_rows: int,
            pos0: int = 0, positions: Optional[torch.Tensor] = None,
            out_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -57,6 +103,7 @@ def add_pe(inp: torch.Tensor, pe: torch.Tensor, alpha: torch.Tensor, out: torch.
     return out
 
 
+@_dev_guard
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
               ada_wb: Optional[torch.Tensor] = None, rows: Optional[torch.Tensor] = None,
               out_dtype: torch.dtype = torch.float32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -73,6 +120,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
+@_dev_guard
 def adaln_project(W: torch.Tensor, b: torch.Tensor, emb: torch.Tensor, out: Optional[torch.Tensor] = None):
     """(weight | bias) = project_layer(stage_embedding)  (transformer.py:96-100)."""
     _req_cuda(W, b, emb)
@@ -84,6 +132,7 @@ def adaln_project(W: torch.Tensor, b: torch.Tensor, emb: torch.Tensor, out: Opti
     return out
 
 
+@_dev_guard
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, epilogue: int = L.VB_EPI_NONE,
            out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """C = epi(A W^T + b)  (F.linear; transformer.py:332-334, activation.py:408, valle.py:1039,1128)."""
@@ -100,12 +149,19 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
+@_dev_guard
 def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, n_head: int,
               mask_mode: int = L.VB_MASK_FULL, text_lens: Optional[torch.Tensor] = None,
               out: Optional[torch.Tensor] = None, seg1_lens: Optional[torch.Tensor] = None,
-              seg1_start: int = 0) -> torch.Tensor:
-    """softmax(q k^T / sqrt(hd) + mask) v over packed ragged sequences (activation.py:408-427)."""
-    _req_cuda(qkv, cu_seqlens, text_lens)
+              seg1_start: int = 0, dense_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T / sqrt(hd) + mask) v over packed ragged sequences (activation.py:408-427).
+    dense_mask: bool / uint8 [L, L] `attn_mask` tensor (True = blocked) for mask_mode VB_MASK_DENSE."""
+    _req_cuda(qkv, cu_seqlens, text_lens, dense_mask)
+    dm_ptr, dm_ld = 0, 0
+    if mask_mode == L.VB_MASK_DENSE:
+        assert dense_mask is not None and dense_mask.dim() == 2
+        dense_mask = dense_mask.to(torch.uint8).contiguous()
+        dm_ptr, dm_ld = dense_mask.data_ptr(), dense_mask.stride(0)
     M, d3 = qkv.shape
     d = d3 // 3
     if out is None:
@@ -113,11 +169,12 @@ def attention(qkv: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int, n_he
     B = cu_seqlens.numel() - 1
     L.check(L.load().vb_attention(qkv.data_ptr(), _DT[qkv.dtype], M, B, n_head, d // n_head, cu_seqlens.data_ptr(),
                                   L.ptr(text_lens), L.ptr(seg1_lens), seg1_start, max_seqlen, mask_mode, out.data_ptr(), 0, 0, 0, 0,
-                                  _stream()),
+                                  dm_ptr, dm_ld, _stream()),
             "vb_attention")
     return out
 
 
+@_dev_guard
 def gather_rows(src: torch.Tensor, rows: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _req_cuda(src, rows)
     d = src.shape[1]
@@ -129,6 +186,7 @@ def gather_rows(src: torch.Tensor, rows: torch.Tensor, out: Optional[torch.Tenso
     return out
 
 
+@_dev_guard
 def nar_argmax_accumulate(logits: torch.Tensor, codes: torch.Tensor, code_row_stride: int,
                           next_emb: Optional[torch.Tensor], y_emb: Optional[torch.Tensor],
                           y_rows: Optional[torch.Tensor] = None) -> None:
@@ -142,6 +200,7 @@ def nar_argmax_accumulate(logits: torch.Tensor, codes: torch.Tensor, code_row_st
             "vb_nar_argmax_accumulate")
 
 
+@_dev_guard
 def cross_entropy_rows(logits: torch.Tensor, targets: torch.Tensor, ignore_index: int = -1) -> torch.Tensor:
     """per-row F.cross_entropy (valle.py:877,936-941); ignored rows give 0."""
     _req_cuda(logits, targets)
