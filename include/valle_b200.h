@@ -53,6 +53,9 @@ int vb_abi_version(void);
 const char *vb_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py gpu_launches) */
 int64_t vb_launch_count(void);
+/* Tuning / A-B switch `name` (the VB_* knobs listed in INTEGRATION.md) for this process; takes precedence over the
+ * environment variable of the same name.  Values are read when kernels are launched (or captured). */
+int vb_tune_set(const char *name, int value);
 /* Profiling builds only (libvalle_b200_trace.so, compiled with -DVB_TRACE): bind a device ring
  * buf[cap] / counter; the kernels of the AR decode step then append (globaltimer_ns << 8 | id) stamps
  * (tools/trace_ar_step.py).  The product library returns VB_ERR_UNSUPPORTED. */
@@ -244,24 +247,29 @@ int vb_gather_rows(const float *src, int64_t src_row_stride, const int32_t *rows
  *      fp32, activations [B, C, T] (time contiguous).
  * ---------------------------------------------------------------------------------------- */
 /* SConv1d: y = conv1d(pad(act(x))) + bias (+ residual); act = ELU if pre_elu; padding (pad_left,
- * pad_right) reflect or zero; w [Cout, Cin, K] (weight-norm already folded, tokenizer.py:181-208). */
-int vb_conv1d(const float *x, int B, int Cin, int Tin, const float *w, const float *bias, int Cout, int K,
+ * pad_right) reflect or zero.  wp: the conv weight [Cout, Cin, K] (weight-norm already folded,
+ * tokenizer.py:181-208) PRE-PACKED channel-fastest as [Cin, K, Cout].
+ * phase > 1 -- the causal SConvTranspose1d with K == 2*stride and the right padding trimmed, as a stride-1 K=2
+ * convolution onto Cout = C * phase "phase channels" c' = c * phase + r: wp[ci][0][c'] = w_T[ci][c][r + phase],
+ * wp[ci][1][c'] = w_T[ci][c][r] (w_T [Cin, C, 2*phase] the transposed-conv weight), pad_left = 1 (zero), bias [C];
+ * output channel c' is stored to out[b, c, t * phase + r], out [B, C, Tout * phase]. */
+int vb_conv1d(const float *x, int B, int Cin, int Tin, const float *wp, const float *bias, int Cout, int K,
               int stride, int dilation, int pad_left, int pad_right, int reflect, int pre_elu,
-              const float *residual, float *out, int Tout, vb_stream_t stream);
-/* causal SConvTranspose1d with K == 2*stride, right padding trimmed: out [B, Cout, Tin*stride];
- * w [Cin, Cout, K] */
-int vb_conv_transpose1d(const float *x, int B, int Cin, int Tin, const float *w, const float *bias, int Cout,
-                        int K, int stride, int pre_elu, float *out, vb_stream_t stream);
+              const float *residual, float *out, int Tout, int phase, vb_stream_t stream);
 /* one LSTM layer over T steps: xproj [T, B, 4H] = W_ih x + b_ih + b_hh (gate order i,f,g,o),
- * whh_t [H, 4H] = W_hh^T, h_seq [T, B, H] out, c_state [B, H] scratch */
+ * whh_t [H, 4H] = W_hh^T, h_seq [T, B, H] out, c_state [B * H + 32] floats of scratch (cell state of the
+ * step-wise path / grid-barrier word of the persistent kernel).  B <= 64: all T steps run in one cooperative
+ * launch (the W_hh slices stay in shared memory); larger batches fall back to one launch per step. */
 int vb_lstm_layer(const float *xproj, const float *whh_t, int T, int B, int H, float *h_seq, float *c_state,
                   vb_stream_t stream);
 /* residual VQ encode of rows x [n_rows, dim]: per stage idx = argmax -(|r|^2 - 2 r.e + |e|^2), r -= e_idx.
  * codebooks [n_q, n_codes, dim], codebooks_t [n_q, dim, n_codes], codebook_sq [n_q, n_codes];
- * codes[row*code_row_stride + q*code_q_stride] (int64) */
+ * The code of row r (sequence s = r / rows_per_seq, frame f = r % rows_per_seq) and stage q is written to
+ * codes[s*code_seq_stride + f*code_row_stride + q*code_q_stride] (int64): [B, n_q, T] codes of a whole batch in one
+ * launch with rows_per_seq = T, strides (n_q*T, 1, T); rows_per_seq <= 0: one sequence. */
 int vb_rvq_encode(const float *x, int64_t n_rows, int dim, int n_q, int n_codes, const float *codebooks,
                   const float *codebooks_t, const float *codebook_sq, int64_t *codes, int64_t code_row_stride,
-                  int64_t code_q_stride, vb_stream_t stream);
+                  int64_t code_q_stride, int64_t rows_per_seq, int64_t code_seq_stride, vb_stream_t stream);
 /* out = in.permute(p0, p1, p2) for a contiguous [d0, d1, d2] fp32 tensor */
 int vb_permute3(const float *in, int d0, int d1, int d2, int p0, int p1, int p2, float *out, vb_stream_t stream);
 

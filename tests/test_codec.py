@@ -55,3 +55,76 @@ def test_audio_tokenizer_requires_weights_and_cuda():
     from valle_b200.data.tokenizer import AudioTokenizer
     with pytest.raises(_lib.VbError):
         AudioTokenizer()
+
+
+def test_random_encodec_weights_have_the_published_architecture():
+    """product-side synthetic weights: same tensors (names, shapes) as transformers' 24 kHz EncodecModel"""
+    from transformers import EncodecConfig, EncodecModel
+    from valle_b200.data.tokenizer import random_encodec_weights
+    sd = random_encodec_weights(0)
+    ref = EncodecModel(EncodecConfig()).state_dict()
+    n_conv = 0
+    for k, v in sd.items():
+        k2 = k.replace(".conv.weight", ".conv.parametrizations.weight.original1")
+        assert k2 in ref and tuple(ref[k2].shape) == tuple(v.shape), k
+        n_conv += k.endswith(".conv.weight")
+    assert n_conv == sum(k.endswith("original1") for k in ref)
+
+
+def test_compute_num_frames_matches_the_hop_count():
+    from valle_b200.data.tokenizer import compute_num_frames
+    for n in (320, 321, 24000, 239999, 240000, 240161, 479):
+        exp = compute_num_frames(round(n / 24000, ndigits=12), 320.0 / 24000, 24000)
+        assert abs(exp - -(-n // 320)) <= 1          # tokenizer.py:305: within one frame of what the codec emits
+
+
+@pytest.mark.gpu
+def test_persistent_lstm_layer_equals_the_stepwise_path():
+    """one cooperative launch for all T steps (W_hh slices resident in shared memory, grid barrier per step) against the
+    launch-per-step kernels: same arithmetic up to the k-group summation order"""
+    from valle_b200 import _lib as L
+    from valle_b200.data.tokenizer import AudioTokenizer
+    m = E.build_codec(0)
+    tok = AudioTokenizer(device="cuda:0", weights=m.state_dict())
+    lstm = [mod for kind, mod in tok.codec.enc if kind == "lstm"][0]
+    g = torch.Generator().manual_seed(8)
+    for B, T in ((5, 37), (16, 75), (64, 20)):
+        x = torch.randn(B, 512, T, generator=g).cuda()
+        a = lstm(x)
+        L.check(L.load().vb_tune_set(b"VB_LSTM_STEPWISE", 1))
+        try:
+            b = lstm(x)
+        finally:
+            L.load().vb_tune_set(b"VB_LSTM_STEPWISE", 0)
+        assert float((a - b).abs().max()) < 2e-5, (B, T, float((a - b).abs().max()))
+
+
+@pytest.mark.gpu
+def test_extract_batch_ragged_waveforms_vs_oracle():
+    """AudioTokenExtractor.extract_batch (tokenizer.py:326-361): ragged waveforms, zero-padded to the batch maximum as
+    the reference does, trimmed to the expected frame count; codes against the HF oracle on the same padded batch."""
+    from valle.data import AudioTokenExtractor, AudioTokenizer
+    m = E.build_codec(0)
+    ext = AudioTokenExtractor(tokenizer=AudioTokenizer(device="cuda:0", weights=m.state_dict()), max_batch=4)
+    g = torch.Generator().manual_seed(4)
+    lens = [24000, 7000, 15321, 9600, 12000]
+    waves = [(torch.randn(1, n, generator=g) * 0.1).clamp(-1, 1) for n in lens]
+    out = ext.extract_batch(waves, 24000, None)
+    assert len(out) == len(lens)
+    single = ext.extract(waves[2], 24000)
+    assert single.shape == out[2].shape
+    order = sorted(range(len(lens)), key=lambda i: -lens[i])
+    agree, total = 0, 0
+    for b0 in range(0, len(order), 4):
+        ids = order[b0:b0 + 4]
+        pad = torch.zeros(len(ids), 1, lens[ids[0]])
+        for j, i in enumerate(ids):
+            pad[j, 0, : lens[i]] = waves[i][0]
+        ref, _ = E.encode(m, pad)                       # [B, 8, T]
+        for j, i in enumerate(ids):
+            o = torch.from_numpy(out[i])                # [T_i, 8]
+            assert o.shape == (-(-lens[i] // 320), 8) or abs(o.shape[0] - -(-lens[i] // 320)) <= 1
+            r = ref[j, :, : o.shape[0]].t()
+            agree += int((o == r).all(dim=1).sum())
+            total += o.shape[0]
+    assert agree / total >= 0.97, agree / total

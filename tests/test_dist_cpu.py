@@ -63,3 +63,57 @@ def test_gather_codes_gloo_world2_ragged():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _worker_fast(rank, world, port, q):
+    """fixed-shape fast path (b_max / g_max given, packed tensor passed) and the sharded tokenisation driver"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from valle_b200.dist import tokenize_sharded
+        n_utts = 6
+        lo, hi = shard_range(n_utts, rank, world)
+
+        def codes_of(u):
+            g = torch.Generator().manual_seed(100 + u)
+            return torch.randint(0, 1024, (4 + u, 8), generator=g)
+
+        mine = [codes_of(u) for u in range(lo, hi)]
+        out, base = gather_codes(mine, 8, torch.device("cpu"), b_max=3, g_max=40, packed=torch.cat(mine), return_base=True)
+        ok = len(out) == n_utts and base.shape == (world, 40, 8)
+        ok = ok and all(torch.equal(out[u], codes_of(u)) for u in range(n_utts))
+
+        class FakeTok:
+            device = torch.device("cpu")
+
+        class FakeCfg:
+            num_quantizers = 8
+
+        class FakeExtractor:   # stands in for AudioTokenExtractor: codes depend only on the waveform
+            tokenizer, config = FakeTok(), FakeCfg()
+
+            def extract_batch_device(self, samples, sr):
+                return [(w.reshape(-1)[: 8 * (w.numel() // 8)].reshape(-1, 8).abs() * 1000).long() % 1024 for w in samples]
+
+        g = torch.Generator().manual_seed(1)
+        waves = [torch.randn(1, 16 * (3 + i), generator=g) for i in range(5)]
+        got = tokenize_sharded(FakeExtractor(), waves, 24000)
+        exp = FakeExtractor().extract_batch_device(waves, 24000)
+        ok = ok and len(got) == 5 and all(torch.equal(a, b) for a, b in zip(got, exp))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_fixed_shape_fast_path_and_sharded_tokenisation_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_fast, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]

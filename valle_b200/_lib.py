@@ -67,6 +67,7 @@ PROTOTYPES = {
     "vb_last_error": (C.c_char_p, []),
     "vb_launch_count": (C.c_int64, []),
     "vb_trace_bind": (C.c_int, [vp, vp, C.c_uint]),
+    "vb_tune_set": (C.c_int, [C.c_char_p, C.c_int]),
     "vb_embed_sum": (C.c_int, [vp, C.c_int64, C.c_int64, C.POINTER(vp), c_i32p, C.c_int, C.c_int64, C.c_int, vp,
                                C.c_int64, vp, C.c_int, vp, vp]),
     "vb_add_pe": (C.c_int, [vp, C.c_int64, vp, C.c_int64, vp, vp, C.c_int64, C.c_int, vp, C.c_int64, vp, vp]),
@@ -89,10 +90,10 @@ PROTOTYPES = {
                                            C.c_int64, vp, C.c_int, vp]),
     "vb_cross_entropy": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int64, vp, vp]),
     "vb_conv1d": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                            C.c_int, C.c_int, vp, vp, C.c_int, vp]),
-    "vb_conv_transpose1d": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+                            C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, vp]),
     "vb_lstm_layer": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]),
-    "vb_rvq_encode": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int64, C.c_int64, vp]),
+    "vb_rvq_encode": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int64, C.c_int64,
+                                C.c_int64, C.c_int64, vp]),
     "vb_permute3": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "vb_gather_rows": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, vp, C.c_int64, vp]),
 }

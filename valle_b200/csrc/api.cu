@@ -23,6 +23,23 @@ void set_error(const char *fmt, ...) {
 }
 void count_launch() { __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED); }
 
+// Tuning knobs: vb_tune_set() overrides > environment variable of the same name > built-in default.  Read at
+// launch time (a captured CUDA graph keeps the values it was captured with).
+namespace {
+struct TuneEntry {
+  char name[48];
+  int value;
+};
+TuneEntry g_tune[32];
+int g_n_tune = 0;
+}  // namespace
+int tune(const char *name, int dflt) {
+  for (int i = 0; i < g_n_tune; ++i)
+    if (strcmp(g_tune[i].name, name) == 0) return g_tune[i].value;
+  const char *e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 #ifdef VB_TRACE
 static trace_bind_fn g_trace_binders[32];
 static int g_n_trace_binders = 0;
@@ -43,6 +60,19 @@ struct vb_decoder {
 VB_API int vb_abi_version(void) { return VB_ABI_VERSION; }
 VB_API const char *vb_last_error(void) { return g_err; }
 VB_API int64_t vb_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+VB_API int vb_tune_set(const char *name, int value) {
+  VB_CHECK_ARG(name && strlen(name) < sizeof(g_tune[0].name), "vb_tune_set: bad name");
+  for (int i = 0; i < g_n_tune; ++i)
+    if (strcmp(g_tune[i].name, name) == 0) {
+      g_tune[i].value = value;
+      return VB_OK;
+    }
+  VB_CHECK_ARG(g_n_tune < 32, "vb_tune_set: table full");
+  strcpy(g_tune[g_n_tune].name, name);
+  g_tune[g_n_tune++].value = value;
+  return VB_OK;
+}
 
 VB_API int vb_trace_bind(unsigned long long *buf, unsigned int *counter, unsigned int cap) {
 #ifdef VB_TRACE
@@ -277,12 +307,13 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
     // enough to fill the SMs is not the optimum for the projections whose partial sums a reduce kernel has to add
     // up again (FFN2: 9 splits beat 18, QKV: 5 beat 6, FFN1: 2 beat 4); 40 % of the KV streams prefetched into L2
     // beat 20 / 60 %.
-    static const int pf_env = getenv("VB_KV_PREFETCH_PCT") ? atoi(getenv("VB_KV_PREFETCH_PCT")) : 40;
+    const int pf_env = tune("VB_KV_PREFETCH_PCT", 40);
     const int pf_pct = B >= 16 ? pf_env : 0;
-    static const int qkv_env = getenv("VB_SPLITS_QKV") ? atoi(getenv("VB_SPLITS_QKV")) : 0;
-    static const int out_splits = getenv("VB_SPLITS_OUT") ? atoi(getenv("VB_SPLITS_OUT")) : 0;   // 0 = fill the SMs
-    static const int ffn1_env = getenv("VB_SPLITS_FFN1") ? atoi(getenv("VB_SPLITS_FFN1")) : 0;
-    static const int ffn2_env = getenv("VB_SPLITS_FFN2") ? atoi(getenv("VB_SPLITS_FFN2")) : 0;
+    const int pf_bulk = tune("VB_KV_PF_BULK", 0);
+    const int qkv_env = tune("VB_SPLITS_QKV", 0);
+    const int out_splits = tune("VB_SPLITS_OUT", 0);   // 0 = fill the SMs
+    const int ffn1_env = tune("VB_SPLITS_FFN1", 0);
+    const int ffn2_env = tune("VB_SPLITS_FFN2", 0);
     const int qkv_splits = qkv_env > 0 ? qkv_env : std::max(1, std::min(5, d / 128));
     const int ffn2_splits = ffn2_env > 0 ? ffn2_env : std::max(1, std::min(9, dff / 128));
     const int ffn1_splits = ffn1_env > 0 ? ffn1_env : std::max(1, std::min(2, d / 128));
@@ -300,6 +331,7 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
       pf.B = B; pf.H = D.n_head; pf.cap = st->cache_cap; pf.row_bytes = (int)(hd * ts);
       pf.text_len = st->text_len; pf.prompt_len = st->prompt_len; pf.n_gen = st->n_gen;
       pf.lo_pct = pf_pct * quarter / 4; pf.hi_pct = pf_pct * (quarter + 1) / 4;
+      pf.bulk = pf_bulk;
       return pf;
     };
     for (int l = 0; l < D.n_layer; ++l) {

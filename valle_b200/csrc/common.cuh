@@ -15,6 +15,7 @@ namespace vb {
 void set_error(const char *fmt, ...);
 extern thread_local int64_t g_launches_tls;
 void count_launch();
+int tune(const char *name, int dflt);  // tuning knob: vb_tune_set() override, else environment variable, else dflt
 
 #define VB_CHECK_ARG(cond, ...)            \
   do {                                     \
@@ -121,6 +122,12 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// asynchronous L2 prefetch of a contiguous byte range by the bulk-copy engine (cp.async.bulk.prefetch.L2, SASS
+// UBLKPF.L2): one instruction, no registers or LSU slots held; p 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
+  if (bytes > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ---- programmatic dependent launch (no-ops unless the launch carries the PDL attribute) -------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
@@ -189,7 +196,7 @@ struct PerDeviceOnce {
 
 // ---- device timeline (profiling builds only: -DVB_TRACE, libvalle_b200_trace.so) ----------------
 // Thread 0 of block (0,0,0) of a traced kernel appends (globaltimer << 8 | id) to a ring bound with
-// vb_trace_bind(); ids: kernel kind * 2 + (0 = dependency resolved, 1 = block 0 done).
+// vb_trace_bind() (the ring keeps the most recent `cap` stamps); ids: kernel kind * 2 + (0 = dependency resolved, 1 = block 0 done).
 #ifdef VB_TRACE
 static __device__ unsigned long long *g_trace_buf = nullptr;
 static __device__ unsigned int *g_trace_cnt = nullptr;
@@ -199,7 +206,7 @@ __device__ __forceinline__ void vb_trace(int id) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     const unsigned i = atomicAdd(g_trace_cnt, 1u);
-    if (i < g_trace_cap) g_trace_buf[i] = (t << 8) | (unsigned long long)(id & 0xff);
+    g_trace_buf[i % g_trace_cap] = (t << 8) | (unsigned long long)(id & 0xff);  // ring: the last cap stamps survive
   }
 }
 typedef int (*trace_bind_fn)(unsigned long long *, unsigned int *, unsigned int);

@@ -36,12 +36,25 @@ struct KvPrefetch {
   int B, H, cap, row_bytes;   // row_bytes = 64 * element size
   const int32_t *text_len, *prompt_len, *n_gen;
   int lo_pct, hi_pct;
+  int bulk;  // 1: one cp.async.bulk.prefetch.L2 per stream slice (lane = stream); 0: one prefetch.global.L2 per line
 };
 // worker = one warp; `n_workers` warps of the grid share the 2 * B * H streams
 __device__ __forceinline__ void kv_prefetch(const KvPrefetch &pf, int worker, int n_workers) {
   if (pf.kbase == nullptr) return;
   const int lane = threadIdx.x & 31;
   const int n_streams = 2 * pf.B * pf.H;
+  if (pf.bulk) {
+    for (int sidx = worker * 32 + lane; sidx < n_streams; sidx += n_workers * 32) {
+      const int pair = sidx >> 1;
+      const int b = pair / pf.H, h = pair - b * pf.H;
+      const int kv = min(pf.text_len[b] + pf.prompt_len[b] + pf.n_gen[b], pf.cap);
+      const int r_lo = kv * pf.lo_pct / 100, r_hi = kv * pf.hi_pct / 100;
+      const char *p = (const char *)((sidx & 1) ? pf.vbase : pf.kbase) + (int64_t)b * pf.seq_stride_bytes +
+                      ((int64_t)h * pf.cap + r_lo) * pf.row_bytes;
+      bulk_prefetch_l2(p, (uint32_t)((r_hi - r_lo) * pf.row_bytes) & ~15u);
+    }
+    return;
+  }
   for (int sidx = worker; sidx < n_streams; sidx += n_workers) {
     const int pair = sidx >> 1;
     const int b = pair / pf.H, h = pair - b * pf.H;

@@ -31,8 +31,9 @@ class _Conv:
     """one SConv1d: folded weight [Cout, Cin, K], bias, stride, dilation."""
 
     def __init__(self, w: torch.Tensor, b: torch.Tensor, stride: int = 1, dilation: int = 1):
-        self.w, self.b, self.stride, self.dilation = w.contiguous(), b.contiguous(), stride, dilation
+        self.b, self.stride, self.dilation = b.contiguous(), stride, dilation
         self.cout, self.cin, self.k = w.shape
+        self.wp = w.permute(1, 2, 0).contiguous()   # [Cin, K, Cout]: the layout the tiled kernel streams
 
     def __call__(self, x: torch.Tensor, pre_elu: bool = False, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         B, Cin, Tin = x.shape
@@ -44,23 +45,32 @@ class _Conv:
         extra = n_frames * self.stride + eff_k - padding_total - Tin
         Tout = (Tin + padding_total + extra - eff_k) // self.stride + 1
         out = torch.empty((B, self.cout, Tout), dtype=torch.float32, device=x.device)
-        L.check(L.load().vb_conv1d(x.data_ptr(), B, Cin, Tin, self.w.data_ptr(), self.b.data_ptr(), self.cout, self.k,
+        L.check(L.load().vb_conv1d(x.data_ptr(), B, Cin, Tin, self.wp.data_ptr(), self.b.data_ptr(), self.cout, self.k,
                                    self.stride, self.dilation, padding_total, extra, 1, int(pre_elu), L.ptr(residual),
-                                   out.data_ptr(), Tout, _stream()), "vb_conv1d")
+                                   out.data_ptr(), Tout, 1, _stream()), "vb_conv1d")
         return out
 
 
 class _ConvT:
+    """causal SConvTranspose1d (K = 2 * stride, right padding trimmed) as a stride-1 two-tap convolution onto
+    Cout * stride phase channels: out[co, q*s + r] = sum_ci x[ci, q] w[ci, co, r] + x[ci, q-1] w[ci, co, r + s]"""
+
     def __init__(self, w: torch.Tensor, b: torch.Tensor, stride: int):
-        self.w, self.b, self.stride = w.contiguous(), b.contiguous(), stride
+        self.b, self.stride = b.contiguous(), stride
         self.cin, self.cout, self.k = w.shape
+        assert self.k == 2 * stride, "EnCodec up-sampling layers have K == 2 * stride"
+        s = stride
+        wp = torch.empty((self.cin, 2, self.cout * s), dtype=w.dtype, device=w.device)
+        wp[:, 0] = w[:, :, s:].reshape(self.cin, self.cout * s)   # tap 0 multiplies x[q - 1]
+        wp[:, 1] = w[:, :, :s].reshape(self.cin, self.cout * s)   # tap 1 multiplies x[q]
+        self.wp = wp.contiguous()
 
     def __call__(self, x: torch.Tensor, pre_elu: bool = False) -> torch.Tensor:
         B, Cin, Tin = x.shape
-        out = torch.empty((B, self.cout, Tin * self.stride), dtype=torch.float32, device=x.device)
-        L.check(L.load().vb_conv_transpose1d(x.data_ptr(), B, Cin, Tin, self.w.data_ptr(), self.b.data_ptr(), self.cout,
-                                             self.k, self.stride, int(pre_elu), out.data_ptr(), _stream()),
-                "vb_conv_transpose1d")
+        s = self.stride
+        out = torch.empty((B, self.cout, Tin * s), dtype=torch.float32, device=x.device)
+        L.check(L.load().vb_conv1d(x.data_ptr(), B, Cin, Tin, self.wp.data_ptr(), self.b.data_ptr(), self.cout * s, 2,
+                                   1, 1, 1, 0, 0, int(pre_elu), 0, out.data_ptr(), Tin, s, _stream()), "vb_conv1d")
         return out
 
 
@@ -90,7 +100,7 @@ class _LSTM:
             H = whh_t.shape[0]
             xproj = ops.linear(inp.view(T * B, -1), w_ih, bias)          # [T*B, 4H]
             h_seq = torch.empty((T, B, H), dtype=torch.float32, device=x.device)
-            c = torch.empty((B, H), dtype=torch.float32, device=x.device)
+            c = torch.empty(B * H + 32, dtype=torch.float32, device=x.device)
             L.check(lib.vb_lstm_layer(xproj.data_ptr(), whh_t.data_ptr(), T, B, H, h_seq.data_ptr(), c.data_ptr(),
                                       _stream()), "vb_lstm_layer")
             inp = h_seq
@@ -121,6 +131,60 @@ def _fold(sd: Dict[str, torch.Tensor], prefix: str) -> Tuple[torch.Tensor, torch
             else sd[prefix + ".weight_v"]
         w = v * (g / v.norm(2, dim=(1, 2), keepdim=True))
     return w.float(), sd[prefix + ".bias"].float()
+
+
+def random_encodec_weights(seed: int = 0, n_q: int = 8) -> Dict[str, torch.Tensor]:
+    """A state dict of the published EnCodec 24 kHz architecture (transformers.EncodecModel key names, plain
+    `.conv.weight` form) with seeded random values: ratios 8*5*4*2, 32 base filters, residual blocks with a k=3 /
+    k=1 pair and a 1x1 shortcut, 2-layer LSTM of 512, 128-dim latents, 1024 x 128 codebooks.  For synthetic
+    benchmarks and smoke tests when no trained weights are at hand (the reference downloads them)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+
+    def conv(prefix, cout, cin, k):
+        bound = 1.0 / math.sqrt(cin * k)
+        sd[prefix + ".conv.weight"] = (torch.rand(cout, cin, k, generator=g) * 2 - 1) * bound
+        sd[prefix + ".conv.bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
+
+    def convt(prefix, cin, cout, k):
+        bound = 1.0 / math.sqrt(cin * k)
+        sd[prefix + ".conv.weight"] = (torch.rand(cin, cout, k, generator=g) * 2 - 1) * bound
+        sd[prefix + ".conv.bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
+
+    def res(prefix, ch):
+        conv(prefix + ".block.1", ch // 2, ch, 3)
+        conv(prefix + ".block.3", ch, ch // 2, 1)
+        conv(prefix + ".shortcut", ch, ch, 1)
+
+    def lstm(prefix, h):
+        b = 1.0 / math.sqrt(h)
+        for i in range(2):
+            for nm, shp in (("weight_ih", (4 * h, h)), ("weight_hh", (4 * h, h)), ("bias_ih", (4 * h,)), ("bias_hh", (4 * h,))):
+                sd[f"{prefix}.lstm.{nm}_l{i}"] = (torch.rand(*shp, generator=g) * 2 - 1) * b
+
+    ratios = EncodecNative.RATIOS
+    ch = 32
+    conv("encoder.layers.0", ch, 1, 7)
+    i = 1
+    for r in reversed(ratios):
+        res(f"encoder.layers.{i}", ch)
+        conv(f"encoder.layers.{i + 2}", 2 * ch, ch, 2 * r)
+        ch *= 2
+        i += 3
+    lstm(f"encoder.layers.{i}", ch)
+    conv(f"encoder.layers.{i + 2}", 128, ch, 7)
+    conv("decoder.layers.0", ch, 128, 7)
+    lstm("decoder.layers.1", ch)
+    i = 2
+    for r in ratios:
+        convt(f"decoder.layers.{i + 1}", ch, ch // 2, 2 * r)
+        ch //= 2
+        res(f"decoder.layers.{i + 2}", ch)
+        i += 3
+    conv(f"decoder.layers.{i + 1}", 1, ch, 7)
+    for q in range(n_q):
+        sd[f"quantizer.layers.{q}.codebook.embed"] = torch.randn(1024, 128, generator=g) * (0.8 ** q)
+    return sd
 
 
 class EncodecNative:
@@ -206,10 +270,10 @@ class EncodecNative:
         lib = L.load()
         L.check(lib.vb_permute3(emb.data_ptr(), B, D, T, 0, 2, 1, rows.data_ptr(), _stream()), "vb_permute3")
         codes = torch.empty((B, self.n_q, T), dtype=torch.int64, device=self.device)
-        for b in range(B):  # codes[b, q, t]: row stride 1 (t), q stride T
-            L.check(lib.vb_rvq_encode(rows[b].data_ptr(), T, D, self.n_q, self.cb.shape[1], self.cb.data_ptr(),
-                                      self.cb_t.data_ptr(), self.cb_sq.data_ptr(), codes[b].data_ptr(), 1, T,
-                                      _stream()), "vb_rvq_encode")
+        # codes[b, q, t] of the whole batch in one launch: frame stride 1, stage stride T, utterance stride n_q * T
+        L.check(lib.vb_rvq_encode(rows.data_ptr(), B * T, D, self.n_q, self.cb.shape[1], self.cb.data_ptr(),
+                                  self.cb_t.data_ptr(), self.cb_sq.data_ptr(), codes.data_ptr(), 1, T, T, self.n_q * T,
+                                  _stream()), "vb_rvq_encode")
         return codes
 
     @torch.no_grad()
@@ -266,3 +330,82 @@ def tokenize_audio(tokenizer: AudioTokenizer, wav: torch.Tensor, sr: int = 24000
         wav = wav.unsqueeze(0)
     with torch.no_grad():
         return tokenizer.encode(wav.to(tokenizer.device))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Dataset-scale tokenisation (valle/data/tokenizer.py:256-361, valle/bin/tokenizer.py:172-214)
+# ---------------------------------------------------------------------------------------------------------------
+def compute_num_frames(duration: float, frame_shift: float, sampling_rate: int) -> int:
+    """lhotse.utils.compute_num_frames as called at tokenizer.py:300-304,349-354 (lhotse is an un-vendored
+    dependency): the number of frames is duration / frame_shift rounded half up."""
+    from decimal import ROUND_HALF_UP, Decimal
+    return int(Decimal(round(duration / frame_shift, ndigits=8)).quantize(0, rounding=ROUND_HALF_UP))
+
+
+class AudioTokenConfig:
+    """tokenizer.py:256-267"""
+
+    def __init__(self, frame_shift: float = 320.0 / 24000, num_quantizers: int = 8):
+        self.frame_shift = frame_shift
+        self.num_quantizers = num_quantizers
+
+    def to_dict(self):
+        return dict(frame_shift=self.frame_shift, num_quantizers=self.num_quantizers)
+
+    @staticmethod
+    def from_dict(data):
+        return AudioTokenConfig(**data)
+
+
+class AudioTokenExtractor:
+    """tokenizer.py:270-361 (an lhotse FeatureExtractor in the reference; lhotse is not a dependency here, the
+    methods lhotse calls -- `extract`, `extract_batch`, `frame_shift`, `feature_dim`, `name`, `config` -- are kept).
+    Waveforms must already be 24 kHz mono (the reference resamples with encodec.utils.convert_audio, :284-290)."""
+    name = "encodec"
+    config_type = AudioTokenConfig
+
+    def __init__(self, config: Optional[AudioTokenConfig] = None, tokenizer: Optional[AudioTokenizer] = None,
+                 device=None, weights=None, max_batch: int = 32):
+        self.config = config or AudioTokenConfig()
+        self.tokenizer = tokenizer or AudioTokenizer(device=device, weights=weights)
+        self.max_batch = max_batch
+
+    @property
+    def frame_shift(self) -> float:
+        return self.config.frame_shift
+
+    def feature_dim(self, sampling_rate: int) -> int:
+        return self.config.num_quantizers
+
+    def _check_rate(self, sampling_rate: int):
+        if sampling_rate != self.tokenizer.sample_rate:
+            raise ValueError(f"valle_b200.AudioTokenExtractor: resample to {self.tokenizer.sample_rate} Hz first")
+
+    def extract(self, samples, sampling_rate: int):
+        """[1, N] waveform -> numpy [T, 8] codes (tokenizer.py:278-307)"""
+        return self.extract_batch([samples], sampling_rate, None)[0]
+
+    def extract_batch_device(self, samples: Sequence, sampling_rate: int) -> List[torch.Tensor]:
+        """codes [T_b, 8] int64 ON THE DEVICE for every waveform: utterances are sorted by length and encoded in
+        zero-padded batches of <= max_batch; each result is trimmed to its expected frame count (:345-357)"""
+        self._check_rate(sampling_rate)
+        dev = self.tokenizer.device
+        waves = [torch.as_tensor(w).reshape(-1).to(torch.float32) for w in samples]
+        order = sorted(range(len(waves)), key=lambda i: -waves[i].numel())
+        out: List[Optional[torch.Tensor]] = [None] * len(waves)
+        for b0 in range(0, len(order), self.max_batch):
+            ids = order[b0:b0 + self.max_batch]
+            n_max = waves[ids[0]].numel()
+            batch = torch.zeros((len(ids), 1, n_max), dtype=torch.float32, device=dev)
+            for j, i in enumerate(ids):
+                batch[j, 0, : waves[i].numel()] = waves[i].to(dev, non_blocking=True)
+            codes = self.tokenizer.encode(batch)[0][0]                       # [B, n_q, T]
+            for j, i in enumerate(ids):
+                n = compute_num_frames(round(waves[i].numel() / sampling_rate, ndigits=12), self.frame_shift, sampling_rate)
+                assert abs(-(-waves[i].numel() // self.tokenizer.codec.hop) - n) <= 1
+                out[i] = codes[j, :, :n].t()                                 # [T, n_q]
+        return out
+
+    def extract_batch(self, samples, sampling_rate: int, lengths=None):
+        """list of waveforms -> list of numpy [T_b, 8] (tokenizer.py:326-361)"""
+        return [c.cpu().numpy() for c in self.extract_batch_device(samples, sampling_rate)]

@@ -170,6 +170,7 @@ class ValleEngine:
         self.sample_on_host = False
         #: micro-batches decoded concurrently on separate streams when B >= 32 (bf16 tensor-core path)
         self.micro_batches = 1
+        self.last_packed: Optional[torch.Tensor] = None
         self.replayed_launches = 0   # kernels executed through CUDA-graph replays
         self.captured_launches = 0   # kernels recorded at capture time (counted by the library, not run)
         self._bufs: Dict[Tuple[int, int, int], _ArBuffers] = {}
@@ -373,6 +374,9 @@ class ValleEngine:
         self.stats.prefill_ms = ev[0].elapsed_time(ev[1])
         self.stats.ar_ms = ev[1].elapsed_time(ev[2])
         self.stats.nar_ms = ev[2].elapsed_time(ev[3])
+        #: the packed [sum(Tgen), Q] device tensor behind the returned per-utterance views (dist.gather_codes ships it
+        #: as is instead of re-packing the views)
+        self.last_packed = codes
         if return_device:
             return [codes[cu_g[b]:cu_g[b + 1]] for b in range(B)]
         host = codes.cpu()

@@ -201,11 +201,13 @@ class VALLE(nn.Module):
     def inference_batch(self, texts: Sequence[torch.Tensor], prompts: Sequence[torch.Tensor],
                         enroll_lens: Optional[Sequence[int]] = None, top_k: int = 1,
                         temperature: float = 1.0, max_new_tokens: Optional[int] = None,
-                        dtype: Optional[torch.dtype] = None) -> List[torch.Tensor]:
+                        dtype: Optional[torch.dtype] = None, return_device: bool = False) -> List[torch.Tensor]:
         """Engine feature (the reference asserts batch 1, valle.py:989): B independent utterances
-        decoded together; result[b] equals `inference()` on utterance b alone."""
+        decoded together; result[b] equals `inference()` on utterance b alone.  Codes come back on the host, or
+        (return_device=True) stay on the GPU, e.g. for the data-parallel gather of valle_b200.dist."""
         return self.engine(dtype).generate(texts, prompts, enroll_lens=enroll_lens, top_k=top_k,
-                                           temperature=temperature, max_new_tokens=max_new_tokens)
+                                           temperature=temperature, max_new_tokens=max_new_tokens,
+                                           return_device=return_device)
 
     @torch.no_grad()
     def continual(self, x: torch.Tensor, x_lens: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
