@@ -169,6 +169,77 @@ int vb_decoder_forward(vb_decoder_t dec, float *x, int64_t M, int B, const int32
                        size_t workspace_bytes, vb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a2 / f2  Training: VALLE.forward with gradients (valle/models/valle.py:762-959; loss.backward() at
+ *     valle/bin/trainer.py:674).  The backward functions produce what torch.autograd produces for the reference's
+ *     modules; parameter gradients are fp32 and ACCUMULATED (+=) into caller-zeroed buffers.
+ * ---------------------------------------------------------------------------------------- */
+/* bytes of the activation store vb_decoder_forward_train fills for M rows (per layer: layer input, LN1 out, q|k|v,
+ * attention out, post-attention residual, LN2 out, FFN hidden) */
+size_t vb_decoder_train_save_bytes(const vb_decoder_desc *desc, int64_t M);
+/* vb_decoder_forward (no KV cache) that keeps the activations the backward pass needs in `save` */
+int vb_decoder_forward_train(vb_decoder_t dec, float *x, int64_t M, int B, const int32_t *cu_seqlens,
+                             const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
+                             int mask_mode, const float *ada_wb, void *save, size_t save_bytes, vb_stream_t stream);
+
+typedef struct vb_layer_grads { /* fp32 gradient buffers of one layer, same shapes as vb_layer_params; NULL = skip */
+  float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b, *lin1_w, *lin1_b, *lin2_w, *lin2_b;
+  float *norm1_w, *norm1_b, *norm2_w, *norm2_b;
+} vb_layer_grads;
+typedef struct vb_layer_wt { /* the four matrices TRANSPOSED, storage dtype (operands of the input-gradient GEMMs) */
+  const void *in_proj_wt;  /* [d, 3d] */
+  const void *out_proj_wt; /* [d, d] */
+  const void *lin1_wt;     /* [d, dff] */
+  const void *lin2_wt;     /* [dff, d] */
+} vb_layer_wt;
+
+size_t vb_decoder_backward_workspace(const vb_decoder_desc *desc, int64_t M);
+/* Backward of vb_decoder_forward_train.  dx: fp32 [M, d], gradient w.r.t. the stack output on entry, w.r.t. the
+ * stack input on return.  ada_wb / dada_wb: the AdaLN (weight|bias) rows of the forward call and their gradient
+ * ([(2*n_layer+1), 2d], rows 2l / 2l+1 touched here), both NULL for a LayerNorm stack.  wt / grads: host arrays
+ * [n_layer]. */
+int vb_decoder_backward(vb_decoder_t dec, float *dx, int64_t M, int B, const int32_t *cu_seqlens,
+                        const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
+                        int mask_mode, const float *ada_wb, float *dada_wb, const void *save, const vb_layer_wt *wt,
+                        const vb_layer_grads *grads, void *workspace, size_t workspace_bytes, vb_stream_t stream);
+
+/* LayerNorm / AdaptiveLayerNorm backward (transformer.py:57-108) of y = vb_layernorm(x rows): dx[xrow(r), :] +=
+ * d/dx, optional copy of the updated dx rows in copy_dtype ([*, d] dense), dgamma / dbeta / dada_wb (2d: weight |
+ * bias) accumulated; any gradient pointer may be NULL. */
+int vb_layernorm_backward(const float *x, int64_t x_row_stride, const int32_t *rows, int64_t n_rows, int d,
+                          const float *gamma, const float *beta, const float *ada_wb, float eps, const float *dy,
+                          int64_t dy_row_stride, float *dx, int64_t dx_row_stride, void *dx_copy, int copy_dtype,
+                          float *dgamma, float *dbeta, float *dada_wb, vb_stream_t stream);
+/* F.cross_entropy backward: dlogits[r, 0:n_vocab] = grad_scale * grad_rows[r] * (softmax - onehot(target)), 0 for
+ * ignored rows; columns [n_vocab, n_out) are zero-filled (K padding of the following GEMMs). */
+int vb_cross_entropy_backward(const float *logits, int64_t ld_logits, const int64_t *targets, int64_t n_rows,
+                              int n_vocab, int64_t ignore_index, const float *grad_rows, float grad_scale, void *dlogits,
+                              int out_dtype, int64_t ld_out, int n_out, vb_stream_t stream);
+/* nn.Embedding backward of vb_embed_sum: table_grads[j][tokens[r, j], :] += dy[dy_row(r), :] */
+int vb_embed_backward(const int64_t *tokens, int64_t tok_row_stride, int64_t tok_tab_stride, float *const *table_grads,
+                      const int32_t *table_rows, int n_tables, int64_t n_rows, int d, const float *dy,
+                      int64_t dy_row_stride, const int32_t *dy_rows, vb_stream_t stream);
+/* out[0] += sum_r <a[r, :], b[pos(r), :]>: gradient of the SinePositionalEmbedding alpha (embedding.py:93-97) */
+int vb_rowdot_accumulate(const float *a, int64_t a_row_stride, const float *b, int64_t pos0, const int32_t *positions,
+                         int64_t n_rows, int d, float *out, vb_stream_t stream);
+/* AdaptiveLayerNorm.project_layer backward for one (weight|bias) row: dW[2d, d] += dwb (x) emb, db[2d] += dwb,
+ * demb[d] += W^T dwb */
+int vb_adaln_project_backward(const float *W, const float *emb, const float *dwb, int d, float *dW, float *db,
+                              float *demb, vb_stream_t stream);
+size_t vb_linear_backward_workspace(int dtype, int64_t M, int N, int K);
+/* Gradients of Y[M,N] = X[M,K] W[N,K]^T + b (vb_linear): dX = dY W computed as linear(dY, Wt) with Wt = W^T [K, N]
+ * (dx_epilogue VB_EPI_NONE, or VB_EPI_RESIDUAL to accumulate into an fp32 dX), dW[N,K] += dY^T X, db[N] += column
+ * sums of dY.  X / dY / Wt share `dtype`; N and K multiples of 64 (pad with zero columns). */
+int vb_linear_backward(const void *X, int dtype, int64_t ldx, const void *Wt, const void *dY, int64_t lddy, void *dX,
+                       int dx_dtype, int64_t lddx, int dx_epilogue, float *dW, float *db, int64_t M, int N, int K,
+                       void *workspace, size_t workspace_bytes, vb_stream_t stream);
+size_t vb_attention_backward_workspace(int64_t M, int n_head);
+/* Backward of vb_attention: qkv / out / dout as in the forward call, dqkv [M, 3d] = (dQ | dK | dV), same dtype */
+int vb_attention_backward(const void *qkv, const void *out, const void *dout, int dtype, int64_t M, int B, int n_head,
+                          int head_dim, const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,
+                          int seg1_start, int max_seqlen, int mask_mode, void *dqkv, void *workspace,
+                          size_t workspace_bytes, vb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * a1  AR sampling loop of VALLE.inference (valle.py:1012-1057) with a growing KV cache,
  *     batched over B independent utterances.  All loop state lives on the device.
  * ---------------------------------------------------------------------------------------- */

@@ -54,6 +54,18 @@ class ArHead(C.Structure):
                 ("pe_rows", C.c_int32), ("greedy", C.c_int32)]
 
 
+class LayerGrads(C.Structure):
+    """vb_layer_grads: fp32 gradient buffers of one layer (accumulated)"""
+    _fields_ = [(n, vp) for n in (
+        "in_proj_w", "in_proj_b", "out_proj_w", "out_proj_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b",
+        "norm1_w", "norm1_b", "norm2_w", "norm2_b")]
+
+
+class LayerWt(C.Structure):
+    """vb_layer_wt: transposed matrices of one layer (storage dtype)"""
+    _fields_ = [(n, vp) for n in ("in_proj_wt", "out_proj_wt", "lin1_wt", "lin2_wt")]
+
+
 class VbError(RuntimeError):
     """a C-ABI call returned a non-zero status, or libvalle_b200.so is missing (there is no fallback path)"""
 
@@ -82,6 +94,26 @@ PROTOTYPES = {
     "vb_decoder_forward_workspace": (C.c_size_t, [C.POINTER(DecoderDesc), C.c_int64]),
     "vb_decoder_forward": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp,
                                      C.c_int64, C.c_int64, C.c_int, vp, C.c_size_t, vp]),
+    "vb_decoder_train_save_bytes": (C.c_size_t, [C.POINTER(DecoderDesc), C.c_int64]),
+    "vb_decoder_forward_train": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp,
+                                           C.c_size_t, vp]),
+    "vb_decoder_backward_workspace": (C.c_size_t, [C.POINTER(DecoderDesc), C.c_int64]),
+    "vb_decoder_backward": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp,
+                                      C.POINTER(LayerWt), C.POINTER(LayerGrads), vp, C.c_size_t, vp]),
+    "vb_layernorm_backward": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, vp, vp, vp, C.c_float, vp, C.c_int64, vp,
+                                        C.c_int64, vp, C.c_int, vp, vp, vp, vp]),
+    "vb_cross_entropy_backward": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int64, vp, C.c_float, vp, C.c_int,
+                                            C.c_int64, C.c_int, vp]),
+    "vb_embed_backward": (C.c_int, [vp, C.c_int64, C.c_int64, C.POINTER(vp), c_i32p, C.c_int, C.c_int64, C.c_int, vp,
+                                    C.c_int64, vp, vp]),
+    "vb_rowdot_accumulate": (C.c_int, [vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_int, vp, vp]),
+    "vb_adaln_project_backward": (C.c_int, [vp, vp, vp, C.c_int, vp, vp, vp, vp]),
+    "vb_linear_backward_workspace": (C.c_size_t, [C.c_int, C.c_int64, C.c_int, C.c_int]),
+    "vb_linear_backward": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, C.c_int64, vp, C.c_int, C.c_int64, C.c_int, vp, vp,
+                                     C.c_int64, C.c_int, C.c_int, vp, C.c_size_t, vp]),
+    "vb_attention_backward_workspace": (C.c_size_t, [C.c_int64, C.c_int]),
+    "vb_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int,
+                                        C.c_int, C.c_int, vp, vp, C.c_size_t, vp]),
     "vb_ar_step_workspace": (C.c_size_t, [C.POINTER(DecoderDesc), C.c_int, C.c_int]),
     "vb_ar_head_step": (C.c_int, [vp, C.POINTER(ArHead), vp, C.POINTER(ArState), vp, C.c_size_t, vp]),
     "vb_ar_decode_step": (C.c_int, [vp, C.POINTER(ArHead), C.POINTER(ArState), vp, C.c_size_t, vp]),

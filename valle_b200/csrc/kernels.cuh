@@ -133,6 +133,13 @@ int launch_ln_reduce(float *x, int64_t ldx, int B, int d, const float *partials,
                      const float *bias, const float *gamma, const float *beta, float eps, bf16 *out16,
                      bool pdl, cudaStream_t s);
 
+// backward.cu
+int launch_transpose_pad(const void *in, int dtype, int64_t ld_in, int64_t R, int C, void *out, int64_t ld_out,
+                         cudaStream_t s);
+int launch_colsum(const void *in, int dtype, int64_t ld, int64_t R, int N, float *out, cudaStream_t s);
+int launch_relu_bwd(void *dh, const void *h, int dtype, int64_t n, cudaStream_t s);
+int launch_cast_from_f32(const float *in, void *out, int dtype, int64_t n, cudaStream_t s);
+
 // sample.cu
 int launch_ar_sample(float *logits, int64_t ld_logits, const float *partials, int splits, int ldp,
                      const vb_ar_head *head, vb_ar_state *st, int d, const int64_t *forced, int reduce_only, bool pdl,

@@ -331,6 +331,20 @@ class NativeDecoder:
             ops.adaln_project(fn.project_layer.weight.detach(), fn.project_layer.bias.detach(), e, tab[r])
         return tab
 
+    def transposed(self):
+        """(vb_layer_wt array, keep-alive list): the four matrices of every layer transposed, in the storage dtype --
+        the weight operands of the input-gradient GEMMs of vb_decoder_backward"""
+        arr = (L.LayerWt * self.n_layer)()
+        keep = []
+        for i, lyr in enumerate(self.enc.layers):
+            for name, p in (("in_proj_wt", lyr.self_attn.in_proj_weight), ("out_proj_wt", lyr.self_attn.out_proj.weight),
+                            ("lin1_wt", lyr.linear1.weight), ("lin2_wt", lyr.linear2.weight)):
+                t = p.detach().to(self.dtype).t().contiguous()
+                keep.append(t)
+                setattr(arr[i], name, t.data_ptr())
+        self._wt_keep = keep
+        return arr, keep
+
     def workspace(self, nbytes: int) -> Tensor:
         if self._ws is None or self._ws.numel() < nbytes:
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)

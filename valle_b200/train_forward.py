@@ -1,10 +1,11 @@
 """VALLE.forward (training loss, valle/models/valle.py:762-959) on the sm_100a kernels.
 
-Forward only (no autograd graph): embeddings + sine PE, the AR stack over padded
-[text | audio] rows with the merged causal/key-padding rule, one NAR stage with AdaLN, the
-prediction heads (tensor-core GEMMs in bf16 mode), cross-entropy and top-10 accuracy.  Used for
-validation / scoring from bin/trainer.py; the backward pass is listed under "next" in DESIGN.md,
-so calling it in training mode raises instead of silently skipping dropout.
+Embeddings + sine PE, the AR stack over padded [text | audio] rows with the merged causal / key-padding rule, one
+NAR stage with AdaLN, the prediction heads (tensor-core GEMMs in bf16 mode), cross-entropy and top-10 accuracy.
+With gradients enabled (bin/trainer.py:525-531,674: `loss = model(...)`, `scaler.scale(loss).backward()`) every step
+goes through the autograd bridges of valle_b200/autograd.py, whose backward runs the gradient kernels of
+csrc/backward.cu; under torch.no_grad() (validation) the same kernels run without recording.  Dropout is not
+applied in training mode (p treated as 0).
 """
 from __future__ import annotations
 
@@ -31,16 +32,23 @@ def _top10(logits: torch.Tensor, targets: torch.Tensor, ignore: int) -> torch.Te
     return hit.sum().float() / keep.sum().clamp(min=1).float()
 
 
-@torch.no_grad()
 def valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, reduction: str = "sum",
                   train_stage: int = 0, **kwargs):
+    """dispatch: with autograd recording if gradients are enabled and any parameter wants one, else forward only"""
+    want_grad = torch.is_grad_enabled() and any(p.requires_grad for p in model.parameters())
+    if want_grad:
+        return _valle_forward(model, x, x_lens, y, y_lens, reduction, train_stage, True, **kwargs)
+    with torch.no_grad():
+        return _valle_forward(model, x, x_lens, y, y_lens, reduction, train_stage, False, **kwargs)
+
+
+def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, reduction: str, train_stage: int,
+                   want_grad: bool, **kwargs):
     """VALLE.forward of valle/models/valle.py:762-959 without the backward pass: AR stage (:807-877, causal mask
     of :835-861 as VB_MASK_PADDED_AR), one random NAR stage (:879-941, prefix modes of _prepare_prompts :335-393),
     cross-entropy with reduction `sum` (:877, :936-941) and the top-10 accuracies; returns ((x, codes), loss, metrics)."""
+    from . import autograd as AG
     from .models.valle import PromptedFeatures
-    if model.training:
-        raise NotImplementedError("valle_b200.VALLE.forward: forward-only (eval mode); the backward pass / "
-                                  "training-mode dropout is not built -- call model.eval()")
     assert x.ndim == 2, x.shape
     assert x_lens.ndim == 1, x_lens.shape
     y_prompts_codes = None
@@ -75,19 +83,34 @@ def valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, reduc
     def embed_pe(tokens, table, pos_mod, T):
         """[N, T] ids -> [N, T, d] = table[ids] + alpha * pe[:T]."""
         tok = tokens.reshape(-1).contiguous()
-        e = torch.empty((tok.numel(), d), dtype=torch.float32, device=dev)
-        ops.embed_sum(tok, 1, 0, [table.detach()], tok.numel(), e)
-        pe = pos_mod.table(T, dev)
-        e = e.view(N, T, d)
-        out = torch.empty_like(e)
-        for b in range(N):
-            ops.add_pe(e[b], pe, pos_mod.alpha.detach(), out[b], T, pos0=0)
-        return out
+        e = AG.EmbedSum.apply(tok, 1, 0, tok.numel(), table)
+        return add_pe(e.view(N, T, d), pos_mod, T)
 
-    def stack(nd, rows, seg1_lens, mode, ada=None, Lp=None):
+    def add_pe(e, pos_mod, T):
+        return AG.AddPe.apply(e, pos_mod.table(T, dev), pos_mod.alpha)
+
+    def stack(enc, nd, rows, seg1_lens, mode, ada=None, Lp=None):
         cu = (torch.arange(N + 1, dtype=torch.int32, device=dev) * Lp).contiguous()
+        if want_grad:
+            return AG.DecoderStack.apply(rows, ada, nd, (cu, N, Lp, mode, xl32, seg1_lens, Smax), *AG.layer_params(enc))
         nd.forward(rows, cu, N, Lp, mode, xl32, ada, seg1_lens=seg1_lens, seg1_start=Smax)
         return rows
+
+    def final_norm(nd, rows, ada, sel):
+        wb = ada[2 * nd.n_layer] if ada is not None else None
+        fn = nd.enc.norm
+        inner = fn.norm if ada is not None else fn
+        return AG.LayerNormRows.apply(rows, inner.weight, inner.bias, wb, sel, inner.eps, dtype)
+
+    def ada_table(enc, nd, stage_weight):
+        if not want_grad:
+            return nd.ada_table(stage_weight)
+        wb = []
+        for lyr in enc.layers:
+            for nm in (lyr.norm1, lyr.norm2):
+                wb += [nm.project_layer.weight, nm.project_layer.bias]
+        wb += [enc.norm.project_layer.weight, enc.norm.project_layer.bias]
+        return AG.AdaTable.apply(stage_weight, *wb)
 
     # ---- AR decoder (valle.py:828-881) ----
     if train_stage in (0, 1):
@@ -95,15 +118,14 @@ def valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, reduc
         ye = embed_pe(yin.contiguous(), model.ar_audio_embedding.weight, model.ar_audio_position, Tmax)
         rows = torch.cat([xe, ye], dim=1).reshape(N * (Smax + Tmax), d).contiguous()
         nd = model.ar_decoder.native(dtype)
-        stack(nd, rows, yl32, L.VB_MASK_PADDED_AR, None, Smax + Tmax)
+        rows = stack(model.ar_decoder, nd, rows, yl32, L.VB_MASK_PADDED_AR, None, Smax + Tmax)
         sel = (torch.arange(N, device=dev)[:, None] * (Smax + Tmax) + Smax
                + torch.arange(Tmax, device=dev)[None, :]).reshape(-1).to(torch.int32).contiguous()
-        hn = nd.final_norm(rows, None, rows=sel, out_dtype=dtype)
-        w = model.ar_predict_layer.weight.detach()
-        logits = ops.linear(hn, w if dtype == torch.float32 else w.to(dtype), None, out_dtype=torch.float32)
+        hn = final_norm(nd, rows, None, sel)
+        logits = AG.Linear.apply(hn, model.ar_predict_layer.weight, dtype)
         tg = targets.reshape(-1).contiguous()
-        total_loss = total_loss + ops.cross_entropy_rows(logits, tg).sum()
-        metrics["ArTop10Accuracy"] = _top10(logits, tg, NUM_AUDIO_TOKENS).item() * y_lens.sum().type(torch.float32)
+        total_loss = total_loss + AG.CrossEntropySum.apply(logits, tg, -1)
+        metrics["ArTop10Accuracy"] = _top10(logits.detach(), tg, NUM_AUDIO_TOKENS).item() * y_lens.sum().type(torch.float32)
         x_emb_out = xe
 
     if Q == 1:
@@ -114,15 +136,13 @@ def valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, reduc
         num_nar_layers = Q - 1
         nar_stage = model.rng.choices([_k for _k in range(1, Q)], weights=[1.0 / num_nar_layers] * num_nar_layers, k=1)[0]
         xe = embed_pe(text, model.nar_text_embedding.weight, model.nar_text_position, Smax)
-        emb = [e.weight.detach() for e in model.nar_audio_embeddings]
+        emb = [e.weight for e in model.nar_audio_embeddings]
         yq = codes[..., 0].contiguous()
         pm = model.prefix_mode
 
         def emb_sum(tok2d, tabs, T):  # [N, T, len(tabs)] ids -> sum_j tabs[j][ids[..., j]] in order
             tok = tok2d.reshape(-1, len(tabs)).contiguous()
-            o = torch.empty((tok.shape[0], d), dtype=torch.float32, device=dev)
-            ops.embed_sum(tok, len(tabs), 1, tabs, tok.shape[0], o)
-            return o.view(N, T, d)
+            return AG.EmbedSum.apply(tok, len(tabs), 1, tok.shape[0], *tabs).view(N, T, d)
 
         if pm == 0:  # valle.py:339-345
             prefix_len = 0
@@ -158,32 +178,27 @@ def valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, reduc
             seg1 = (yl32 + (Ty - Tmax)).contiguous()   # key mask F.pad(y_mask, (prefix, 0), False) valle.py:908-914
         elif pm == 1:
             tg = tg[:, prefix_len:]
-        pe = model.nar_audio_position.table(Ty, dev)
-        y_pos = torch.empty((N, Ty, d), dtype=torch.float32, device=dev)
-        y_emb = y_emb.contiguous()
-        for b in range(N):
-            ops.add_pe(y_emb[b], pe, model.nar_audio_position.alpha.detach(), y_pos[b], Ty, pos0=0)
+        y_pos = add_pe(y_emb.contiguous(), model.nar_audio_position, Ty)
         Lp = Smax + Ty
         rows = torch.cat([xe, y_pos], dim=1).reshape(N * Lp, d).contiguous()
         nd = model.nar_decoder.native(dtype)
-        ada = nd.ada_table(model.nar_stage_embeddings[nar_stage - 1].weight)
-        stack(nd, rows, seg1, L.VB_MASK_PADDED, ada, Lp)
+        ada = ada_table(model.nar_decoder, nd, model.nar_stage_embeddings[nar_stage - 1].weight)
+        rows = stack(model.nar_decoder, nd, rows, seg1, L.VB_MASK_PADDED, ada, Lp)
         off = Smax + prefix_len
         if pm == 4:
             off = Smax + prefix_len
         Tt = Lp - off
         sel = (torch.arange(N, device=dev)[:, None] * Lp + off
                + torch.arange(Tt, device=dev)[None, :]).reshape(-1).to(torch.int32).contiguous()
-        hn = nd.final_norm(rows, ada, rows=sel, out_dtype=dtype)
-        w = model.nar_predict_layers[nar_stage - 1].weight.detach()
-        logits = ops.linear(hn, w if dtype == torch.float32 else w.to(dtype), None, out_dtype=torch.float32)
+        hn = final_norm(nd, rows, ada, sel)
+        logits = AG.Linear.apply(hn, model.nar_predict_layers[nar_stage - 1].weight, dtype)
         tgf = tg.reshape(-1).contiguous()
         if pm == 4:
             prefix_len = 0  # reset for the metric / loss rescale (valle.py:927-928)
         total_length = y_lens.sum().type(torch.float32)
-        ce = ops.cross_entropy_rows(logits, tgf, ignore_index=NUM_AUDIO_TOKENS).sum()
+        ce = AG.CrossEntropySum.apply(logits, tgf, NUM_AUDIO_TOKENS)
         total_loss = total_loss + ce * (total_length / (total_length - prefix_len * N))
-        lp = F.pad(logits, (0, 1), value=logits.min().item())   # valle.py:946-950
+        lp = F.pad(logits.detach(), (0, 1), value=logits.min().item())   # valle.py:946-950
         metrics["NarTop10Accuracy"] = _top10(lp, tgf, NUM_AUDIO_TOKENS).item() * total_length
         x_emb_out = xe
     if train_stage == 0:
