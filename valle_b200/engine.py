@@ -171,6 +171,8 @@ class ValleEngine:
         #: micro-batches decoded concurrently on separate streams when B >= 32 (bf16 tensor-core path)
         self.micro_batches = 1
         self.last_packed: Optional[torch.Tensor] = None
+        #: batches of 1..4 utterances (bf16, greedy) decode inside the persistent small-batch kernel
+        self.small_batch_kernel = True
         self.replayed_launches = 0   # kernels executed through CUDA-graph replays
         self.captured_launches = 0   # kernels recorded at capture time (counted by the library, not run)
         self._bufs: Dict[Tuple[int, int, int], _ArBuffers] = {}
@@ -331,11 +333,16 @@ class ValleEngine:
         steps = 0
         while steps < max_steps:
             n = min(poll, max_steps - steps)
-            for _ in range(n):
-                fs = None
-                if forced_steps is not None:
-                    fs = forced_steps[min(steps + 1, forced_steps.shape[0] - 1)]
-                self._decode_step(buf, head, greedy, top_k, temperature, fs)
+            if greedy and trace is None and self.dtype == torch.bfloat16 and B <= 4 and self.small_batch_kernel:
+                # 1..4 utterances: n decode steps inside ONE persistent cooperative kernel (csrc/decode_small.cu)
+                L.check(self.lib.vb_ar_decode_steps(self.ar.handle, C.byref(head), C.byref(buf.st), buf.ws.data_ptr(),
+                                                    buf.ws.numel(), n, L.stream_ptr()), "vb_ar_decode_steps")
+            else:
+                for _ in range(n):
+                    fs = None
+                    if forced_steps is not None:
+                        fs = forced_steps[min(steps + 1, forced_steps.shape[0] - 1)]
+                    self._decode_step(buf, head, greedy, top_k, temperature, fs)
             steps += n
             self._join_views(buf)
             if trace is not None and want(steps):  # poll == 1 here: the logits row of iteration `steps`
