@@ -21,8 +21,10 @@ from oracle import valle_oracle as O
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
-AR_TOL = 0.12    # max abs logit error of a bf16 AR step vs the fp32 reference (logit scale ~ +-3)
-NAR_TOL = 0.15   # same for a NAR stage
+AR_TOL = 0.12      # max abs logit error of a bf16 AR step vs the fp32 reference (AR logits: std 0.58, |max| 2.4)
+NAR_TOL_REL = 0.03  # NAR stages: max abs error relative to the standard deviation of that stage's reference logits
+                    # (stages 0..5 project onto the N(0,1)-initialised tied embedding tables: std ~25, |max| ~95;
+                    # the untied last stage: std 0.5)
 
 
 def _model(g, dtype):
@@ -96,12 +98,13 @@ def test_bf16_teacher_forced_logits_vs_fp32_oracle_big_short():
     nerr = []
     for i in range(7):
         e = (nar[i] - tr.nar_logits[i]).abs().amax(dim=1)       # per frame
-        nerr.append(float(e.max()))
-        assert float(e.max()) < NAR_TOL, (i, float(e.max()))
+        scale = float(tr.nar_logits[i].std())
+        nerr.append(float(e.max()) / scale)
+        assert float(e.max()) < NAR_TOL_REL * scale, (i, float(e.max()), scale)
         f = nar_arg[i] != ref[:, i + 1]
         assert not bool((f & (tr.nar_margin[i] > 2 * e)).any()), f"NAR stage {i}: flip outside a near-tie"
     _report("big_short_teacher_forced", dict(ar_max_abs_err=float(err.max()), ar_mean_abs_err=float(err.mean()),
-                                              ar_argmax_flips=int(flips.sum()), ar_steps=n, nar_max_abs_err=nerr,
+                                              ar_argmax_flips=int(flips.sum()), ar_steps=n, nar_max_err_over_std=nerr,
                                               nar_argmax_flips=[int((nar_arg[i] != ref[:, i + 1]).sum()) for i in range(7)]))
 
 
@@ -127,12 +130,13 @@ def test_bf16_teacher_forced_vs_fp32_engine_config1():
     nerr = []
     for i in range(7):
         e = (nar[i] - nar32[i]).abs().amax(dim=1)
-        nerr.append(float(e.max()))
-        assert float(e.max()) < NAR_TOL, (i, float(e.max()))
+        scale = float(nar32[i].std())
+        nerr.append(float(e.max()) / scale)
+        assert float(e.max()) < NAR_TOL_REL * scale, (i, float(e.max()), scale)
         f = nar_arg[i] != ref[:, i + 1]
         assert not bool((f & (g["nar_margin"][i] > 2 * e + 6e-4)).any()), f"NAR stage {i}: flip outside a near-tie"
     _report("config1_teacher_forced", dict(ar_max_abs_err=float(err.max()), ar_mean_abs_err=float(err.mean()),
-                                            ar_argmax_flips=int(flips.sum()), ar_steps=n, nar_max_abs_err=nerr,
+                                            ar_argmax_flips=int(flips.sum()), ar_steps=n, nar_max_err_over_std=nerr,
                                             nar_argmax_flips=[int((nar_arg[i] != ref[:, i + 1]).sum()) for i in range(7)]))
 
 
