@@ -335,7 +335,7 @@ int vb_conv1d(const float *x, int B, int Cin, int Tin, const float *wp, const fl
               int stride, int dilation, int pad_left, int pad_right, int reflect, int pre_elu,
               const float *residual, float *out, int Tout, int phase, vb_stream_t stream);
 /* one LSTM layer over T steps: xproj [T, B, 4H] = W_ih x + b_ih + b_hh (gate order i,f,g,o),
- * whh_t [H, 4H] = W_hh^T, h_seq [T, B, H] out, c_state [B * H + 32] floats of scratch (cell state of the
+ * whh_t [H, 4H] = W_hh^T, h_seq [T, B, H] out, c_state [B * H + 64] floats of scratch (cell state of the
  * step-wise path / grid-barrier word of the persistent kernel).  B <= 64: all T steps run in one cooperative
  * launch (the W_hh slices stay in shared memory); larger batches fall back to one launch per step. */
 int vb_lstm_layer(const float *xproj, const float *whh_t, int T, int B, int H, float *h_seq, float *c_state,

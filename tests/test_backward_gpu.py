@@ -70,11 +70,13 @@ def test_layernorm_backward_vs_autograd(adaptive):
     (y * dy).sum().backward()
     dx = torch.full((M, d), 0.25, device=DEV)                    # accumulate semantics: dx += ...
     dg, db_, dwb = torch.zeros(d, device=DEV), torch.zeros(d, device=DEV), torch.zeros(2 * d, device=DEV)
-    xd = x.detach().to(DEV)
-    L.check(lib.vb_layernorm_backward(xd.data_ptr(), d, rows.to(DEV).data_ptr(), 200, d, g.detach().to(DEV).data_ptr(),
-                                      b.detach().to(DEV).data_ptr(), wb.detach().to(DEV).data_ptr() if adaptive else 0, 1e-5,
-                                      dy.to(DEV).data_ptr(), d, dx.data_ptr(), d, 0, L.VB_F32, dg.data_ptr(), db_.data_ptr(),
-                                      dwb.data_ptr() if adaptive else 0, _s()))
+    # (device copies are kept in variables: a temporary's memory may be reused before the kernel runs)
+    xd, rd, gd, bd, dyd = x.detach().to(DEV), rows.to(DEV), g.detach().to(DEV), b.detach().to(DEV), dy.to(DEV)
+    wbd = wb.detach().to(DEV) if adaptive else None
+    L.check(lib.vb_layernorm_backward(xd.data_ptr(), d, rd.data_ptr(), 200, d, gd.data_ptr(), bd.data_ptr(),
+                                      wbd.data_ptr() if adaptive else 0, 1e-5, dyd.data_ptr(), d, dx.data_ptr(), d, 0,
+                                      L.VB_F32, dg.data_ptr(), db_.data_ptr(), dwb.data_ptr() if adaptive else 0, _s()))
+    torch.cuda.synchronize()
     assert _rel(dx.cpu() - 0.25, x.grad) < 2e-5
     assert _rel(dg.cpu(), g.grad) < 2e-5 and _rel(db_.cpu(), b.grad) < 2e-5
     if adaptive:
@@ -126,18 +128,20 @@ def test_attention_backward_vs_autograd(mode, dtype, tol):
         ref_d[r0:r0 + n] = blk.grad
         ref_o[r0:r0 + n] = o.detach()
     from valle_b200 import ops
-    qd = qkv.to(DEV)
-    out = ops.attention(qd, cu.to(DEV), max(lens), H, mm, tl.to(DEV) if tl is not None else None,
-                        seg1_lens=sl.to(DEV) if sl is not None else None, seg1_start=seg1_start)
+    qd, cud, doutd = qkv.to(DEV), cu.to(DEV), dout.to(DEV)
+    tld = tl.to(DEV) if tl is not None else None
+    sld = sl.to(DEV) if sl is not None else None
+    out = ops.attention(qd, cud, max(lens), H, mm, tld, seg1_lens=sld, seg1_start=seg1_start)
     assert _rel(out.float().cpu(), ref_o) < (3e-5 if dtype == torch.float32 else 2e-2)
     dq = torch.empty_like(qd)
     nb = lib.vb_attention_backward_workspace(M, H)
     ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
     dt = L.VB_F32 if dtype == torch.float32 else L.VB_BF16
-    L.check(lib.vb_attention_backward(qd.data_ptr(), out.data_ptr(), dout.to(DEV).data_ptr(), dt, M, B, H, 64,
-                                      cu.to(DEV).data_ptr(), tl.to(DEV).data_ptr() if tl is not None else 0,
-                                      sl.to(DEV).data_ptr() if sl is not None else 0, seg1_start, max(lens), mm,
+    L.check(lib.vb_attention_backward(qd.data_ptr(), out.data_ptr(), doutd.data_ptr(), dt, M, B, H, 64,
+                                      cud.data_ptr(), tld.data_ptr() if tld is not None else 0,
+                                      sld.data_ptr() if sld is not None else 0, seg1_start, max(lens), mm,
                                       dq.data_ptr(), ws.data_ptr(), nb, _s()))
+    torch.cuda.synchronize()
     assert _rel(dq.float().cpu(), ref_d) < tol, _rel(dq.float().cpu(), ref_d)
 
 

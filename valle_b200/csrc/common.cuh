@@ -128,6 +128,41 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) 
   if (bytes > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// ---- grid-wide barrier of a cooperative launch (every CTA resident).  `ctr` is a monotonic arrival counter zeroed
+// before the launch; `target` (thread 0) advances by gridDim.x per barrier.  mode 0: every CTA polls the counter with
+// ld.acquire (simplest, but ~150 pollers hammer one L2 line and delay the late arrivals' atomics); mode 1: polling
+// with nanosleep back-off; mode 2: the LAST arriver publishes a generation word that the others poll, so the counter
+// line only sees one atomic per CTA.
+__device__ __forceinline__ void grid_barrier_sync(unsigned *ctr, unsigned &target, int mode) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned G = gridDim.x * gridDim.y * gridDim.z;
+    target += G;
+    if (mode == 2) {
+      unsigned *gen = ctr + 32;   // a different 128-byte line
+      unsigned prev;
+      asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(ctr) : "memory");
+      if (prev + 1 == target) {
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gen), "r"(target) : "memory");
+      } else {
+        unsigned v;
+        do {
+          __nanosleep(20);
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gen) : "memory");
+        } while ((int)(v - target) < 0);
+      }
+    } else {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+      unsigned v;
+      do {
+        if (mode == 1) __nanosleep(40);
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      } while ((int)(v - target) < 0);
+    }
+  }
+  __syncthreads();
+}
+
 // ---- programmatic dependent launch (no-ops unless the launch carries the PDL attribute) -------
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {

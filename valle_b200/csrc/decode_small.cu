@@ -45,7 +45,7 @@ struct Params {
   int64_t layer_stride, seq_stride;
   int cap;
   float *q, *hb, *part_o, *part_ml;   // scratch: [B][d], [B][dff], [B*H*ns][64], [B*H*ns][2]
-  int ns, n_steps, wbuf_bytes;
+  int ns, n_steps, wbuf_bytes, barrier_mode;
   unsigned *sync;                      // grid-barrier counter, zeroed by the host before the launch
 };
 
@@ -71,18 +71,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                : "memory");
 }
 
-__device__ __forceinline__ void grid_barrier(unsigned *sync, unsigned &target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    target += gridDim.x;
-    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(sync) : "memory");
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(sync) : "memory");
-    } while ((int)(v - target) < 0);
-  }
-  __syncthreads();
-}
+#define grid_barrier(sync, target) grid_barrier_sync(sync, target, P.barrier_mode)
 
 // the current token's K / V rows were written by other CTAs one barrier ago: read through L2
 __device__ __forceinline__ uint4 ld_cg16(const void *p) {
@@ -271,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
       const vb_layer_params &LP = P.L[l];
       bf16 *kc = P.kcache + (int64_t)l * P.layer_stride;
       bf16 *vc = P.vcache + (int64_t)l * P.layer_stride;
+      vb_trace(TR_LN * 2);
       // ---- S1: LN1 + in-proj; q to scratch, k / v appended to the cache (activation.py:408) ----
       load_layernorm<NB>(P.x, B, d, LP.norm1_w, LP.norm1_b, xs, red);
       with_weights(g0 + 4 * l + 0, [&](const bf16 *wsm, int rows, int row0, int K) {
@@ -291,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
       });
       grid_barrier(P.sync, target);
       // ---- S2: single-query attention, one (row, head, KV split) per CTA ----
+      vb_trace(TR_ATTN * 2);
       {
         const int ns = P.ns, item = cta;
         if (item < B * H * ns) {
@@ -308,10 +299,16 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
 #pragma unroll
           for (int i = 0; i < 8; ++i) qf[i] = qs[j8 + i];
           float lmax = -CUDART_INF_F;
-          for (int base = 0; base < n; base += 32) {
-            const int key = base + warp * 4 + g8;
+          for (int base0 = 0; base0 < n; base0 += 128) {
+           uint4 kraw[4];
+#pragma unroll
+           for (int u = 0; u < 4; ++u)   // all loads of the batch in flight before the first use
+             kraw[u] = ld_cg16(kb + (int64_t)(c0 + min(base0 + u * 32 + warp * 4 + g8, n - 1)) * HD + j8);
+#pragma unroll
+           for (int u = 0; u < 4; ++u) {
+            const int key = base0 + u * 32 + warp * 4 + g8;
             float kf[8];
-            unpack8(ld_cg16(kb + (int64_t)(c0 + min(key, n - 1)) * HD + j8), kf);
+            unpack8(kraw[u], kf);
             float dot = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) dot = fmaf(qf[i], kf[i], dot);
@@ -322,6 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
               sc[key] = dot;
               lmax = fmaxf(lmax, dot);
             }
+           }
           }
           lmax = warp_max(lmax);
           if (lane == 0) red[warp] = lmax;
@@ -347,12 +345,19 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
           float acc[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-          for (int key = jl; key < n; key += 32) {
-            float vf[8];
-            unpack8(ld_cg16(vb_ + (int64_t)(c0 + key) * HD + eg), vf);
-            const float pv = sc[key];
+          for (int key0 = jl; key0 < n; key0 += 128) {
+            uint4 vraw[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(pv, vf[i], acc[i]);
+            for (int u = 0; u < 4; ++u) vraw[u] = ld_cg16(vb_ + (int64_t)(c0 + min(key0 + u * 32, n - 1)) * HD + eg);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int key = key0 + u * 32;
+              float vf[8];
+              unpack8(vraw[u], vf);
+              const float pv = key < n ? sc[key] : 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) acc[i] = fmaf(pv, vf[i], acc[i]);
+            }
           }
           __syncthreads();                       // scores consumed: reuse `sc` as the [32][65] reduction tile
           float *rt = sc;
@@ -373,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
       }
       grid_barrier(P.sync, target);
       // ---- S3: combine the KV splits (every CTA, from L2), out-proj + bias + residual ----
+      vb_trace(TR_GEMM * 2);
       for (int i = tid; i < B * d; i += kThreads) {
         const int b = i / d, c = i - b * d, h = c / HD, e = c - h * HD;
         const int64_t p0 = ((int64_t)b * H + h) * P.ns;
@@ -400,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
       });
       grid_barrier(P.sync, target);
       // ---- S4: LN2 + linear1 + ReLU (transformer.py:332-334) ----
+      vb_trace(TR_RELU * 2);
       load_layernorm<NB>(P.x, B, d, LP.norm2_w, LP.norm2_b, xs, red);
       with_weights(g0 + 4 * l + 2, [&](const bf16 *wsm, int rows, int row0, int K) {
         gemv_smem<NB>(wsm, rows, K, xs, [&](int r, int b, float v) {
@@ -410,6 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
       });
       grid_barrier(P.sync, target);
       // ---- S5: linear2 + bias + residual ----
+      vb_trace(TR_COMBINE * 2);
       for (int i = tid; i < NB * dff; i += kThreads) xs[i] = (i < B * dff) ? __ldcg(P.hb + i) : 0.f;
       __syncthreads();
       with_weights(g0 + 4 * l + 3, [&](const bf16 *wsm, int rows, int row0, int K) {
@@ -423,6 +431,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
       grid_barrier(P.sync, target);
     }
     // ---- final LayerNorm + ar_predict_layer (valle.py:1039) ----
+    vb_trace(TR_FUSED * 2);
     load_layernorm<NB>(P.x, B, d, P.fn_w, P.fn_b, xs, red);
     with_weights(g0 + 4 * P.n_layer, [&](const bf16 *wsm, int rows, int row0, int K) {
       gemv_smem<NB>(wsm, rows, K, xs, [&](int r, int b, float v) {
@@ -431,6 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
     });
     grid_barrier(P.sync, target);
     // ---- sampler: argmax, stop rule, append, next input row (valle.py:1044-1057, 1013-1015); CTA b per row ----
+    vb_trace(TR_SAMPLE * 2);
     if (cta < B) {
       const int b = cta;
       float *xo = P.x + (int64_t)b * d;
@@ -508,7 +518,7 @@ size_t decode_small_workspace(const vb_decoder_desc &D, int B) {
   const int G = sm_count();
   const int ns = std::max(1, G / (std::max(1, B) * D.n_head));
   return align_up((size_t)B * D.d_model * 4, 256) + align_up((size_t)B * D.d_ff * 4, 256) +
-         align_up((size_t)B * D.n_head * ns * (sm::HD + 2) * 4, 256) + 256;
+         align_up((size_t)B * D.n_head * ns * (sm::HD + 2) * 4, 256) + 512;
 }
 
 int launch_decode_small(const vb_decoder_desc &D, const vb_layer_params *layers, const vb_ar_head *head, vb_ar_state *st,
@@ -532,6 +542,7 @@ int launch_decode_small(const vb_decoder_desc &D, const vb_layer_params *layers,
   P.layer_stride = st->cache_layer_stride; P.seq_stride = st->cache_seq_stride; P.cap = st->cache_cap;
   P.ns = std::max(1, G / (B * D.n_head));
   P.n_steps = n_steps;
+  P.barrier_mode = tune("VB_GRID_BARRIER", 2);
   P.wbuf_bytes = small_wbuf_bytes(D, head->n_vocab, G);
   char *p = (char *)scratch;
   P.q = (float *)p;        p += align_up((size_t)B * d * 4, 256);
@@ -539,7 +550,7 @@ int launch_decode_small(const vb_decoder_desc &D, const vb_layer_params *layers,
   P.part_o = (float *)p;   p += align_up((size_t)B * D.n_head * P.ns * sm::HD * 4, 256);
   P.part_ml = (float *)p;  p += align_up((size_t)B * D.n_head * P.ns * 2 * 4, 256);
   P.sync = (unsigned *)p;
-  VB_CUDA(cudaMemsetAsync(P.sync, 0, sizeof(unsigned), s));
+  VB_CUDA(cudaMemsetAsync(P.sync, 0, 64 * sizeof(unsigned), s));
   const int NB = B == 1 ? 1 : (B == 2 ? 2 : 4);
   const size_t smem = 2 * (size_t)P.wbuf_bytes + (size_t)NB * std::max(d, dff) * 4 + (sm::kMaxChunk + 64) * 4 + 128 * 4 + 64;
   VB_CHECK_ARG(smem <= 220 * 1024, "decode_small: needs %zu bytes of shared memory", smem);

@@ -165,22 +165,11 @@ lstm_step_kernel(const float *__restrict__ xproj_t, const float *__restrict__ wh
 // The launch per time step of lstm_step_kernel (2 x 750 launches per 10 s utterance batch) becomes 2 launches.
 constexpr int LSTM_U = 4, LSTM_C = 4 * LSTM_U, LSTM_MAXB = 64;
 
-__device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-    } while (v < target);
-  }
-  __syncthreads();
-}
 
 __global__ void __launch_bounds__(256, 1)
 lstm_layer_persistent_kernel(const float *__restrict__ xproj /*[T][B][4H]*/, const float *__restrict__ whh_t /*[H][4H]*/,
-                             int T, int B, int H, float *__restrict__ h_seq /*[T][B][H]*/, unsigned *__restrict__ sync) {
+                             int T, int B, int H, float *__restrict__ h_seq /*[T][B][H]*/, unsigned *__restrict__ sync,
+                             int barrier_mode) {
   extern __shared__ __align__(16) float sm[];
   const int HP = H + 1;                      // padded row of the h tile (bank spread over batch rows)
   float *wsl = sm;                           // [H][LSTM_C]  column c = gate * LSTM_U + u
@@ -202,6 +191,7 @@ lstm_layer_persistent_kernel(const float *__restrict__ xproj /*[T][B][4H]*/, con
   const int kper = (H + kgroups - 1) / kgroups;
   const int tile = tid % tiles, kg = tid / tiles;
   const int bt = tile / (LSTM_C / 4), ct = tile - bt * (LSTM_C / 4);
+  unsigned bar_target = 0;
   __syncthreads();
   for (int t = 0; t < T; ++t) {
     float acc[4][4];
@@ -254,7 +244,7 @@ lstm_layer_persistent_kernel(const float *__restrict__ xproj /*[T][B][4H]*/, con
       cst[i] = cn;
       h_seq[((int64_t)t * B + b) * H + u0 + u] = so * tanhf(cn);
     }
-    if (t + 1 < T) grid_barrier(sync, (unsigned)(t + 1) * gridDim.x);
+    if (t + 1 < T) grid_barrier_sync(sync, bar_target, barrier_mode);
   }
 }
 
@@ -431,11 +421,13 @@ VB_API int vb_lstm_layer(const float *xproj, const float *whh_t, int T, int B, i
   if (B <= ec::LSTM_MAXB && grid_p <= sm_count() && smem_p <= 200 * 1024 && tune("VB_LSTM_STEPWISE", 0) == 0) {
     // all T steps in one cooperative launch; the grid-barrier word lives behind the cell-state scratch
     unsigned *sync = reinterpret_cast<unsigned *>(c_state + (size_t)B * H);
-    VB_CUDA(cudaMemsetAsync(sync, 0, sizeof(unsigned), s));
+    VB_CUDA(cudaMemsetAsync(sync, 0, 64 * sizeof(unsigned), s));
+    int barrier_mode = tune("VB_GRID_BARRIER", 2);
     auto kern = ec::lstm_layer_persistent_kernel;
     static PerDeviceOnce once;
     if (once.first()) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    void *args[] = {(void *)&xproj, (void *)&whh_t, (void *)&T, (void *)&B, (void *)&H, (void *)&h_seq, (void *)&sync};
+    void *args[] = {(void *)&xproj, (void *)&whh_t, (void *)&T, (void *)&B, (void *)&H, (void *)&h_seq, (void *)&sync,
+                    (void *)&barrier_mode};
     VB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid_p), dim3(256), args, smem_p, s));
     count_launch();
     return VB_OK;

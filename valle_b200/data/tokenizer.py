@@ -100,7 +100,7 @@ class _LSTM:
             H = whh_t.shape[0]
             xproj = ops.linear(inp.view(T * B, -1), w_ih, bias)          # [T*B, 4H]
             h_seq = torch.empty((T, B, H), dtype=torch.float32, device=x.device)
-            c = torch.empty(B * H + 32, dtype=torch.float32, device=x.device)
+            c = torch.empty(B * H + 64, dtype=torch.float32, device=x.device)
             L.check(lib.vb_lstm_layer(xproj.data_ptr(), whh_t.data_ptr(), T, B, H, h_seq.data_ptr(), c.data_ptr(),
                                       _stream()), "vb_lstm_layer")
             inp = h_seq
