@@ -176,9 +176,7 @@ def _oracle_grads(g, stage, nar_stage, prefix_len):
     fw = g["forward"]
     loss, _ = O.forward_train(sd, cfg, fw["x"], fw["x_lens"], fw["y"].long(), fw["y_lens"], nar_stage, prefix_len,
                               train_stage=stage)
-    if stage == 0:
-        loss = loss / 2.0   # valle.py:956-957
-    loss.backward()
+    loss.backward()          # (forward_train already halves the stage-0 loss, valle.py:956-957)
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items()}
     return float(loss), grads
 

@@ -235,7 +235,9 @@ def test_finished_rows_leave_their_kv_cache_untouched():
         n_rows = S[short] + prompts[short].shape[0] + outs[short].shape[0]
         a = k_after[:, :, :n_rows].float()
         b = buf1.kcache[:, 0, :, :n_rows].float()
-        tol = 0 if dtype == torch.float32 else 0.05   # bf16: batched (tensor-core) vs batch-1 reduction order
+        # the batched and the batch-1 decode use different reduction orders (fp32: 4-row vs 1-row GEMV; bf16: tensor
+        # cores vs the persistent small-batch kernel); a finished row overwritten by later steps would be off by O(1)
+        tol = 1e-5 if dtype == torch.float32 else 0.05
         assert float((a - b).abs().max()) <= tol
         assert bool(torch.isfinite(buf.x_cur).all())
         if dtype == torch.float32:

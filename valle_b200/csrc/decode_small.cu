@@ -106,11 +106,14 @@ __device__ __forceinline__ WStage wstage(const Params &P, int idx) {
 __device__ __forceinline__ int rows_per_cta(int N) { return (N + gridDim.x - 1) / gridDim.x; }
 
 // out(row r of this CTA, b) = sum_k wsm[r][k] * xs[b][k]: one warp per row, lanes over k (16-byte weight reads)
-template <int NB, typename Epi>
-__device__ __forceinline__ void gemv_smem(const bf16 *wsm, int rows, int K, const float *xs, Epi epi) {
+// `pre(r)` fetches what the epilogue of row r needs from global memory (bias, residual) BEFORE the dot product, so
+// the L2 round trip overlaps the reduction instead of following it
+template <int NB, typename Pre, typename Epi>
+__device__ __forceinline__ void gemv_smem(const bf16 *wsm, int rows, int K, const float *xs, Pre pre, Epi epi) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = warp; r < rows; r += kWarps) {
     const bf16 *wr = wsm + (size_t)r * K;
+    const auto c = pre(r);
     float acc[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = 0.f;
@@ -135,10 +138,14 @@ __device__ __forceinline__ void gemv_smem(const bf16 *wsm, int rows, int K, cons
     for (int b = 0; b < NB; ++b) acc[b] = warp_sum(acc[b]);
     if (lane == 0) {
 #pragma unroll
-      for (int b = 0; b < NB; ++b) epi(r, b, acc[b]);
+      for (int b = 0; b < NB; ++b) epi(r, b, acc[b], c);
     }
   }
 }
+template <int NB> struct RowConst {   // bias of the row + the residual-stream value of every batch row
+  float bias;
+  float res[NB];
+};
 
 // xs[b][:] = LayerNorm(x[b][:]) for the B rows (transformer.py:57-74); x read from L2 (written by other CTAs)
 template <int NB>
@@ -208,6 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
   float *red = sc + kMaxChunk + 64;                                              // [0,32) reductions, [32,96) query
   uint64_t *wbar = reinterpret_cast<uint64_t *>(red + 128);                      // [2]
   __shared__ int s_all_done, s_tok, s_pos;
+  __shared__ int s_kvpos[4], s_fin[4];   // per step: cache row of the current token, stop flag of every batch row
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x;
   const int stages_per_step = 4 * P.n_layer + 1;
@@ -249,11 +257,17 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
 
   for (int step = 0; step < P.n_steps; ++step) {
     const int g0 = step * stages_per_step;
-    if (tid == 0) {
-      int done = 1;
-      for (int b = 0; b < B; ++b) done &= (__ldcg(P.finished + b) != 0);
-      s_all_done = done;
+    if (tid < 4) {
+      int fin = 1, pos = 0;
+      if (tid < B) {
+        fin = __ldcg(P.finished + tid);
+        pos = max(0, min(P.text_len[tid] + P.prompt_len[tid] + __ldcg(P.n_gen + tid) - 1, P.cap - 1));
+      }
+      s_fin[tid] = fin;
+      s_kvpos[tid] = pos;
     }
+    __syncthreads();
+    if (tid == 0) s_all_done = (s_fin[0] != 0) && (s_fin[1] != 0) && (s_fin[2] != 0) && (s_fin[3] != 0);
     __syncthreads();
     if (s_all_done) break;   // uniform over the grid: `finished` only changes in the sampler, a barrier ago
     for (int l = 0; l < P.n_layer; ++l) {
@@ -264,18 +278,17 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
       // ---- S1: LN1 + in-proj; q to scratch, k / v appended to the cache (activation.py:408) ----
       load_layernorm<NB>(P.x, B, d, LP.norm1_w, LP.norm1_b, xs, red);
       with_weights(g0 + 4 * l + 0, [&](const bf16 *wsm, int rows, int row0, int K) {
-        gemv_smem<NB>(wsm, rows, K, xs, [&](int r, int b, float v) {
+        gemv_smem<NB>(wsm, rows, K, xs, [&](int r) { return LP.in_proj_b[row0 + r]; },
+                      [&](int r, int b, float v, float bias) {
           if (b >= B) return;
           const int n = row0 + r;
-          v += LP.in_proj_b[n];
+          v += bias;
           const int part = n / d, c = n - part * d;
           if (part == 0) {
             P.q[(int64_t)b * d + c] = v;
-          } else if (__ldcg(P.finished + b) == 0) {
+          } else if (s_fin[b] == 0) {
             const int h = c / HD, e = c - h * HD;
-            int pos = P.text_len[b] + P.prompt_len[b] + __ldcg(P.n_gen + b) - 1;
-            pos = max(0, min(pos, P.cap - 1));
-            (part == 1 ? kc : vc)[(int64_t)b * P.seq_stride + ((int64_t)h * P.cap + pos) * HD + e] = __float2bfloat16_rn(v);
+            (part == 1 ? kc : vc)[(int64_t)b * P.seq_stride + ((int64_t)h * P.cap + s_kvpos[b]) * HD + e] = __float2bfloat16_rn(v);
           }
         });
       });
@@ -286,15 +299,25 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
         const int ns = P.ns, item = cta;
         if (item < B * H * ns) {
           const int sp = item % ns, bh = item / ns, h = bh % H, b = bh / H;
-          const int kv_len = max(1, min(P.text_len[b] + P.prompt_len[b] + __ldcg(P.n_gen + b), P.cap));
+          const int kv_len = s_kvpos[b] + 1;
           const int chunk = ((kv_len + ns - 1) / ns + 15) & ~15;
           const int c0 = sp * chunk, n = max(0, min(kv_len, c0 + chunk) - c0);
           const bf16 *kb = kc + (int64_t)b * P.seq_stride + (int64_t)h * P.cap * HD;
           const bf16 *vb_ = vc + (int64_t)b * P.seq_stride + (int64_t)h * P.cap * HD;
           float *qs = red + 32;   // [64] staged query
+          const int g8 = lane >> 3, j8 = (lane & 7) * 8;
+          const int eg = (tid & 7) * 8, jl = tid >> 3;
+          // the first 128 keys' K and V rows and the query in ONE L2 / HBM round trip (the cache rows do not depend on q)
+          uint4 k_first[4], v_first[4];
+          if (n > 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              k_first[u] = ld_cg16(kb + (int64_t)(c0 + min(u * 32 + warp * 4 + g8, n - 1)) * HD + j8);
+              v_first[u] = ld_cg16(vb_ + (int64_t)(c0 + min(jl + u * 32, n - 1)) * HD + eg);
+            }
+          }
           if (tid < HD) qs[tid] = __ldcg(P.q + (int64_t)b * d + h * HD + tid) * 0.125f;
           __syncthreads();
-          const int g8 = lane >> 3, j8 = (lane & 7) * 8;
           float qf[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) qf[i] = qs[j8 + i];
@@ -303,7 +326,8 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
            uint4 kraw[4];
 #pragma unroll
            for (int u = 0; u < 4; ++u)   // all loads of the batch in flight before the first use
-             kraw[u] = ld_cg16(kb + (int64_t)(c0 + min(base0 + u * 32 + warp * 4 + g8, n - 1)) * HD + j8);
+             kraw[u] = base0 == 0 ? k_first[u]
+                                  : ld_cg16(kb + (int64_t)(c0 + min(base0 + u * 32 + warp * 4 + g8, n - 1)) * HD + j8);
 #pragma unroll
            for (int u = 0; u < 4; ++u) {
             const int key = base0 + u * 32 + warp * 4 + g8;
@@ -341,14 +365,14 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
 #pragma unroll
           for (int w = 0; w < kWarps; ++w) lt += red[w];
           // O = P V: thread = (8 head dims eg, key lane jl of 32)
-          const int eg = (tid & 7) * 8, jl = tid >> 3;
           float acc[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[i] = 0.f;
           for (int key0 = jl; key0 < n; key0 += 128) {
             uint4 vraw[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) vraw[u] = ld_cg16(vb_ + (int64_t)(c0 + min(key0 + u * 32, n - 1)) * HD + eg);
+            for (int u = 0; u < 4; ++u)
+              vraw[u] = key0 == jl ? v_first[u] : ld_cg16(vb_ + (int64_t)(c0 + min(key0 + u * 32, n - 1)) * HD + eg);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int key = key0 + u * 32;
@@ -379,41 +403,65 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
       grid_barrier(P.sync, target);
       // ---- S3: combine the KV splits (every CTA, from L2), out-proj + bias + residual ----
       vb_trace(TR_GEMM * 2);
-      for (int i = tid; i < B * d; i += kThreads) {
-        const int b = i / d, c = i - b * d, h = c / HD, e = c - h * HD;
-        const int64_t p0 = ((int64_t)b * H + h) * P.ns;
-        float m = -CUDART_INF_F;
-        for (int s = 0; s < P.ns; ++s) m = fmaxf(m, __ldcg(P.part_ml + (p0 + s) * 2));
-        float lt = 0.f, o = 0.f;
-        for (int s = 0; s < P.ns; ++s) {
-          const float ms = __ldcg(P.part_ml + (p0 + s) * 2);
-          if (ms == -CUDART_INF_F) continue;
-          const float w = expf(ms - m);
-          lt += __ldcg(P.part_ml + (p0 + s) * 2 + 1) * w;
-          o += __ldcg(P.part_o + (p0 + s) * HD + e) * w;
+      {
+        // pass 1 (one L2 round trip): the (m, l) pair of every (row, head, split) -> normalised split weights
+        float *wgt = sc;                                 // [B * H * ns]
+        const int n_items = B * H * P.ns;
+        for (int i = tid; i < n_items; i += kThreads) {
+          const float2 ml = __ldcg(reinterpret_cast<const float2 *>(P.part_ml) + i);
+          wgt[i] = ml.x;
+          wgt[n_items + i] = ml.y;
         }
-        xs[b * d + c] = lt > 0.f ? o / lt : 0.f;
+        __syncthreads();
+        for (int bh = tid; bh < B * H; bh += kThreads) {
+          float m = -CUDART_INF_F;
+          for (int s = 0; s < P.ns; ++s) m = fmaxf(m, wgt[bh * P.ns + s]);
+          float lt = 0.f;
+          for (int s = 0; s < P.ns; ++s) {
+            const float ms = wgt[bh * P.ns + s];
+            const float w = (ms == -CUDART_INF_F) ? 0.f : __expf(ms - m);
+            lt += wgt[n_items + bh * P.ns + s] * w;
+            wgt[bh * P.ns + s] = w;
+          }
+          const float inv = lt > 0.f ? 1.f / lt : 0.f;
+          for (int s = 0; s < P.ns; ++s) wgt[bh * P.ns + s] *= inv;
+        }
+        __syncthreads();
+        // pass 2 (one round trip, independent loads): att[b][h*64+e] = sum_s w_s o_s[e]
+        for (int i = tid; i < B * d; i += kThreads) {
+          const int b = i / d, c = i - b * d, hh = c / HD, e = c - hh * HD;
+          const int bh = b * H + hh;
+          const float *po = P.part_o + (int64_t)bh * P.ns * HD + e;
+          float o = 0.f;
+#pragma unroll 4
+          for (int s = 0; s < P.ns; ++s) o = fmaf(__ldcg(po + s * HD), wgt[bh * P.ns + s], o);
+          xs[b * d + c] = o;
+        }
+        for (int i = B * d + tid; i < NB * d; i += kThreads) xs[i] = 0.f;
+        __syncthreads();
       }
-      for (int i = B * d + tid; i < NB * d; i += kThreads) xs[i] = 0.f;
-      __syncthreads();
       with_weights(g0 + 4 * l + 1, [&](const bf16 *wsm, int rows, int row0, int K) {
-        gemv_smem<NB>(wsm, rows, K, xs, [&](int r, int b, float v) {
-          if (b >= B) return;
-          const int n = row0 + r;
-          float *xp = P.x + (int64_t)b * d + n;
-          *xp = __ldcg(xp) + v + LP.out_proj_b[n];
-        });
+        gemv_smem<NB>(wsm, rows, K, xs,
+                      [&](int r) {
+                        RowConst<NB> c;
+                        c.bias = LP.out_proj_b[row0 + r];
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) c.res[b] = b < B ? __ldcg(P.x + (int64_t)b * d + row0 + r) : 0.f;
+                        return c;
+                      },
+                      [&](int r, int b, float v, const RowConst<NB> &c) {
+                        if (b < B) P.x[(int64_t)b * d + row0 + r] = c.res[b] + v + c.bias;
+                      });
       });
       grid_barrier(P.sync, target);
       // ---- S4: LN2 + linear1 + ReLU (transformer.py:332-334) ----
       vb_trace(TR_RELU * 2);
       load_layernorm<NB>(P.x, B, d, LP.norm2_w, LP.norm2_b, xs, red);
       with_weights(g0 + 4 * l + 2, [&](const bf16 *wsm, int rows, int row0, int K) {
-        gemv_smem<NB>(wsm, rows, K, xs, [&](int r, int b, float v) {
-          if (b >= B) return;
-          const int n = row0 + r;
-          P.hb[(int64_t)b * dff + n] = fmaxf(v + LP.lin1_b[n], 0.f);
-        });
+        gemv_smem<NB>(wsm, rows, K, xs, [&](int r) { return LP.lin1_b[row0 + r]; },
+                      [&](int r, int b, float v, float bias) {
+                        if (b < B) P.hb[(int64_t)b * dff + row0 + r] = fmaxf(v + bias, 0.f);
+                      });
       });
       grid_barrier(P.sync, target);
       // ---- S5: linear2 + bias + residual ----
@@ -421,12 +469,17 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
       for (int i = tid; i < NB * dff; i += kThreads) xs[i] = (i < B * dff) ? __ldcg(P.hb + i) : 0.f;
       __syncthreads();
       with_weights(g0 + 4 * l + 3, [&](const bf16 *wsm, int rows, int row0, int K) {
-        gemv_smem<NB>(wsm, rows, K, xs, [&](int r, int b, float v) {
-          if (b >= B) return;
-          const int n = row0 + r;
-          float *xp = P.x + (int64_t)b * d + n;
-          *xp = __ldcg(xp) + v + LP.lin2_b[n];
-        });
+        gemv_smem<NB>(wsm, rows, K, xs,
+                      [&](int r) {
+                        RowConst<NB> c;
+                        c.bias = LP.lin2_b[row0 + r];
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) c.res[b] = b < B ? __ldcg(P.x + (int64_t)b * d + row0 + r) : 0.f;
+                        return c;
+                      },
+                      [&](int r, int b, float v, const RowConst<NB> &c) {
+                        if (b < B) P.x[(int64_t)b * d + row0 + r] = c.res[b] + v + c.bias;
+                      });
       });
       grid_barrier(P.sync, target);
     }
@@ -434,9 +487,10 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
     vb_trace(TR_FUSED * 2);
     load_layernorm<NB>(P.x, B, d, P.fn_w, P.fn_b, xs, red);
     with_weights(g0 + 4 * P.n_layer, [&](const bf16 *wsm, int rows, int row0, int K) {
-      gemv_smem<NB>(wsm, rows, K, xs, [&](int r, int b, float v) {
-        if (b < B) P.logits[(int64_t)b * P.ld_logits + row0 + r] = v;
-      });
+      gemv_smem<NB>(wsm, rows, K, xs, [&](int) { return 0; },
+                    [&](int r, int b, float v, int) {
+                      if (b < B) P.logits[(int64_t)b * P.ld_logits + row0 + r] = v;
+                    });
     });
     grid_barrier(P.sync, target);
     // ---- sampler: argmax, stop rule, append, next input row (valle.py:1044-1057, 1013-1015); CTA b per row ----

@@ -54,22 +54,25 @@ conv1d_tiled_kernel(const float *__restrict__ x, int Cin, int Tin, const float *
     const int cin = min(CI_T, Cin - ci0);
     // weights of this chunk: rows (ci, k) of wp are Cout floats wide
     for (int idx = tid; idx < cin * K * CO_T; idx += 256) {
-      const int row = idx / CO_T, co = idx - row * CO_T;
+      const int row = idx / CO_T, co = idx & (CO_T - 1);   // CO_T is a power of two
       ws[idx] = (co0 + co < Cout) ? wp[((int64_t)ci0 * K + row) * Cout + co0 + co] : 0.f;
     }
-    for (int idx = tid; idx < cin * in_w; idx += 256) {
-      const int ci = idx / in_w, i = idx - ci * in_w;
-      int g = g0 + i;
-      float v = 0.f;
-      if (reflect) {  // F.pad(mode="reflect") index map (pads are < Tin on this path)
-        if (g < 0) g = -g;
-        if (g >= Tin) g = 2 * (Tin - 1) - g;
+    for (int ci = 0; ci < cin; ++ci) {   // (no integer division in the staging loop: it runs once per input element)
+      const float *xrow = xb + (int64_t)(ci0 + ci) * Tin;
+      float *xd = xs + ci * in_w;
+      for (int i = tid; i < in_w; i += 256) {
+        int g = g0 + i;
+        float v = 0.f;
+        if (reflect) {  // F.pad(mode="reflect") index map (pads are < Tin on this path)
+          if (g < 0) g = -g;
+          if (g >= Tin) g = 2 * (Tin - 1) - g;
+        }
+        if (g >= 0 && g < Tin) {
+          v = xrow[g];
+          if (pre_elu) v = elu1(v);
+        }
+        xd[i] = v;
       }
-      if (g >= 0 && g < Tin) {
-        v = xb[(int64_t)(ci0 + ci) * Tin + g];
-        if (pre_elu) v = elu1(v);
-      }
-      xs[idx] = v;
     }
     __syncthreads();
     for (int ci = 0; ci < cin; ++ci) {

@@ -171,6 +171,8 @@ class ValleEngine:
         #: micro-batches decoded concurrently on separate streams when B >= 32 (bf16 tensor-core path)
         self.micro_batches = 1
         self.last_packed: Optional[torch.Tensor] = None
+        #: greedy decode steps captured per CUDA graph (one replay per group; the stop flags are polled every `poll` steps)
+        self.steps_per_graph = 8
         #: batches of 1..4 utterances (bf16, greedy) decode inside the persistent small-batch kernel
         self.small_batch_kernel = True
         self.replayed_launches = 0   # kernels executed through CUDA-graph replays
@@ -337,6 +339,14 @@ class ValleEngine:
                 # 1..4 utterances: n decode steps inside ONE persistent cooperative kernel (csrc/decode_small.cu)
                 L.check(self.lib.vb_ar_decode_steps(self.ar.handle, C.byref(head), C.byref(buf.st), buf.ws.data_ptr(),
                                                     buf.ws.numel(), n, L.stream_ptr()), "vb_ar_decode_steps")
+            elif greedy and self.use_cuda_graph and not self._use_views(buf, greedy):
+                # whole groups of `steps_per_graph` decode steps as one graph replay (no launch gap between the
+                # steps of a group), the remainder one step at a time
+                done = 0
+                while done < n:
+                    k = self.steps_per_graph if n - done >= self.steps_per_graph else 1
+                    self._replay_steps(buf, head, k)
+                    done += k
             else:
                 for _ in range(n):
                     fs = None
@@ -484,6 +494,28 @@ class ValleEngine:
         self._launch_step(buf, head)
         if not greedy:
             self._sample_push(buf, head, top_k, temperature, forced_step)
+
+    def _replay_steps(self, buf: _ArBuffers, head: L.ArHead, k: int):
+        """k greedy decode steps as ONE CUDA graph (captured on first use per (buffer, head tables, k))"""
+        key = (head.pe, head.predict_w, head.audio_emb, k)
+        graphs = buf.__dict__.setdefault("graphs", {})
+        ent = graphs.get(key)
+        if ent is None:
+            if any(kk[:3] != key[:3] for kk in graphs):
+                graphs.clear()                      # tables moved: the old captures hold stale pointers
+            for _ in range(k):
+                self._launch_step(buf, head)        # warm-up launches (function attributes) == these k steps
+            g = torch.cuda.CUDAGraph()
+            n0 = self.lib.vb_launch_count()
+            with torch.cuda.graph(g):
+                for _ in range(k):
+                    self._launch_step(buf, head)
+            kernels = self.lib.vb_launch_count() - n0
+            self.captured_launches += kernels
+            graphs[key] = (g, kernels, head)        # keep the head struct alive
+            return                                  # the warm-up launches were these steps
+        ent[0].replay()
+        self.replayed_launches += ent[1]
 
     def _launch_step(self, buf, head: L.ArHead):
         L.check(self.lib.vb_ar_decode_step(self.ar.handle, C.byref(head), C.byref(buf.st), buf.ws.data_ptr(),
