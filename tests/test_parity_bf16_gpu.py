@@ -21,7 +21,8 @@ from oracle import valle_oracle as O
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
-AR_TOL = 0.12      # max abs logit error of a bf16 AR step vs the fp32 reference (AR logits: std 0.58, |max| 2.4)
+AR_TOL = 0.03      # max abs logit error of a bf16 AR step vs the fp32 reference (AR logits: std 0.58, |max| 2.4;
+                   # measured 0.0099 over the 754 steps of configs[1], profiles/round2_parity_bf16.json)
 NAR_TOL_REL = 0.03  # NAR stages: max abs error relative to the standard deviation of that stage's reference logits
                     # (stages 0..5 project onto the N(0,1)-initialised tied embedding tables: std ~25, |max| ~95;
                     # the untied last stage: std 0.5)
@@ -314,33 +315,3 @@ def test_bf16_small_batch_persistent_kernel_matches_the_launch_chain(fixture, n_
     assert agree >= len(out_small) - 1, agree
     if fixture == "big_short.pt":      # full-size model: most of the 97 frames agree between the two bf16 paths
         assert float((out_small[0][:, 0] == out_chain[0][:, 0]).float().mean()) > 0.5
-
-
-def test_bf16_tensor_core_decode_attention_matches_the_cuda_core_kernel():
-    """The KV-cache attention of the decode step on mma.sync (q and P as bf16 hi + lo pairs against the bf16 cache)
-    against the two-phase CUDA-core kernel on the same cache: same arithmetic up to the summation order, so the
-    logits of every decode step of a ragged batch agree to 2e-3 and the greedy ids are the same; batch 1 (split-KV
-    + combine) and batch 12 (one CTA per (row, head)) are both covered, contexts cross several 16-key blocks."""
-    from valle_b200 import _lib as L
-    lib = L.load()
-    g = load_golden("tiny_batch.pt")
-    m = _model(g, torch.bfloat16)
-    eng = m.engine()
-    eng.small_batch_kernel = False
-    for rep in (1, 3):
-        texts = [u["x"][0] for u in g["utts"]][: (1 if rep == 1 else 4)] * rep
-        prompts = [u["y"][0] for u in g["utts"]][: (1 if rep == 1 else 4)] * rep
-        res = {}
-        for flag in (1, 0):
-            L.check(lib.vb_tune_set(b"VB_ATTN_DECODE_MMA", flag))
-            eng._bufs.clear()
-            tr = {"steps": "all"}
-            out = eng.generate(texts, prompts, top_k=1, trace=tr, max_new_tokens=60)
-            res[flag] = (out, tr["ar_logits"])
-        lib.vb_tune_set(b"VB_ATTN_DECODE_MMA", 1)
-        eng._bufs.clear()
-        n = min(len(res[0][1]), len(res[1][1]))
-        same_ids = all(torch.equal(a, b) for a, b in zip(res[0][0], res[1][0]))
-        worst = max(float((res[0][1][i] - res[1][1][i]).abs().max()) for i in range(min(n, 8)))
-        assert worst < 2e-3, worst
-        assert same_ids or worst < 2e-3

@@ -632,289 +632,6 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
   vb_trace(TR_ATTN * 2 + 1);
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// bf16 KV-cache attention with the dot products on the tensor cores.
-// The two-phase CUDA-core kernel above issues ~15 warp instructions per 128-byte cache row (bf16 unpack, FFMA,
-// shuffle reductions): at B = 64 it sits at ~70 % issue utilisation exactly where HBM saturates, so rows that the
-// projection chain has already pulled into L2 are consumed no faster than rows from HBM.  Here a warp streams
-// 16-key blocks (K 2 KB + V 2 KB) with cp.async into a private, swizzled, double-buffered shared-memory tile and
-// lets mma.sync.m16n8k16 do the arithmetic: S = q K^T with q as row 0 of the A operand (the accumulator layout of
-// row 0 is exactly the A layout of the following P V product), q and P split into bf16 hi + lo parts so that the
-// products see fp32 q / P against the bf16 cache as before.  ~2.5 warp instructions per cache row; three warps per
-// (utterance, head) keep their own online-softmax state and are merged once, together with the current token
-// (served from shared memory, never read back from the cache).
-// ------------------------------------------------------------------------------------------------------------
-namespace dmma {
-constexpr int kWarps = 3, kThreads = kWarps * 32, kBlk = 16;
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                         uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t *>(&v);
-}
-// hi = bf16(x), lo = bf16(x - hi): x ~ hi + lo to ~2^-17 relative
-__device__ __forceinline__ void split2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
-  const float h0 = __bfloat162float(__float2bfloat16_rn(x0)), h1 = __bfloat162float(__float2bfloat16_rn(x1));
-  hi = pack_bf16(h0, h1);
-  lo = pack_bf16(x0 - h0, x1 - h1);
-}
-}  // namespace dmma
-
-__global__ void __launch_bounds__(dmma::kThreads, 7)
-attn_decode_mma_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, bf16 *__restrict__ kcache,
-                       bf16 *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
-                       const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
-                       const int32_t *__restrict__ n_gen, const int32_t *__restrict__ finished,
-                       float *__restrict__ out, bf16 *__restrict__ out16, float *__restrict__ part_o,
-                       float *__restrict__ part_ml, int nsplit) {
-  using namespace dmma;
-  __shared__ __align__(128) bf16 tile[kWarps][2][2][kBlk * HD];   // [warp][stage][K | V][16 keys x 64]
-  __shared__ __align__(16) float qs[HD];
-  __shared__ __align__(16) float knew[HD];
-  __shared__ __align__(16) float vnew[HD];
-  __shared__ float wm[kWarps + 1], wl[kWarps + 1], wo[kWarps + 1][HD];
-  pdl_launch_dependents();
-  const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int d = n_head * HD;
-  bf16 *kb = kcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
-  bf16 *vb_ = vcache + (int64_t)b * cache_seq_stride + (int64_t)h * cache_cap * HD;
-  const bool has_new = qp.part != nullptr;
-  float qbias[3] = {0.f, 0.f, 0.f};
-  if (tid < HD && has_new) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) qbias[j] = qp.bias[j * d + h * HD + tid];
-  }
-  // chunk geometry (lengths of earlier tokens do not depend on this step's kernels; re-validated after the wait)
-  int kv_len, pos, c0, n, nk, nblk;
-  auto geometry = [&](int n_generated) {
-    kv_len = max(1, min(text_len[b] + prompt_len[b] + n_generated, cache_cap));
-    pos = kv_len - 1;
-    const int chunk = ((kv_len + nsplit - 1) / nsplit + 15) & ~15;
-    c0 = sp * chunk;
-    n = max(0, min(kv_len, c0 + chunk) - c0);
-    const bool new_here = has_new && pos >= c0 && pos < c0 + n;
-    nk = new_here ? n - 1 : n;      // keys served from the cache (the current token comes from shared memory)
-    nblk = (nk + kBlk - 1) / kBlk;
-  };
-  // one 16-key block of K and V -> this warp's stage `st` (rows past the chunk re-read its last key; masked later)
-  auto fetch = [&](int blk, int st) {
-    const uint32_t sk = (uint32_t)__cvta_generic_to_shared(&tile[warp][st][0][0]);
-    const uint32_t sv = (uint32_t)__cvta_generic_to_shared(&tile[warp][st][1][0]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int id = lane + 32 * i, row = id >> 3, c = id & 7;
-      const int key = c0 + min(blk * kBlk + row, max(nk - 1, 0));
-      const uint32_t off = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
-      cp_async16(sk + off, kb + (int64_t)key * HD + c * 8);
-      cp_async16(sv + off, vb_ + (int64_t)key * HD + c * 8);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  const int n_gen_early = has_new ? n_gen[b] : -1;
-  if (has_new) {
-    geometry(n_gen_early);
-    if (warp < nblk) fetch(warp, 0);       // first block in flight across the dependency wait and the prologue
-  }
-  pdl_wait();
-  vb_trace(TR_ATTN * 2);
-  if (decode_row_finished(finished, b, h, sp, d, tid, nsplit, n_head, out, out16, part_o, part_ml)) {
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    return;
-  }
-  int n_gen_now;
-  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(n_gen_now) : "l"(n_gen + b) : "memory");
-  bool refetch = !has_new;
-  if (n_gen_now != n_gen_early) {   // uniform over the CTA
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    geometry(n_gen_now);
-    refetch = true;
-  }
-  if (refetch && warp < nblk) fetch(warp, 0);
-  if (tid < HD) {
-    if (has_new) {
-      float a[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int col = j * d + h * HD + tid;
-        const float *p = qp.part + (int64_t)b * qp.ldp + col;
-        float acc = __ldcg(p);
-        for (int s = 1; s < qp.splits; ++s) acc += __ldcg(p + (int64_t)s * 64 * qp.ldp);
-        a[j] = acc + qbias[j];
-      }
-      qs[tid] = a[0] * 0.125f;
-      const bf16 k16 = __float2bfloat16_rn(a[1]), v16 = __float2bfloat16_rn(a[2]);
-      knew[tid] = __bfloat162float(k16);  // exactly what later steps will read back from the cache
-      vnew[tid] = __bfloat162float(v16);
-      if (sp == 0) {
-        kb[(int64_t)pos * HD + tid] = k16;
-        vb_[(int64_t)pos * HD + tid] = v16;
-      }
-    } else {
-      qs[tid] = q[(int64_t)b * d + h * HD + tid] * 0.125f;
-    }
-  }
-  __syncthreads();
-  // Q as row 0 of the A operand, split into bf16 hi + lo: a0 = (row g, k 2t..2t+1), a2 = (row g, k 2t+8..2t+9)
-  uint32_t qh[4][2], ql[4][2];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (g == 0) {
-      split2(qs[16 * j + 2 * t], qs[16 * j + 2 * t + 1], qh[j][0], ql[j][0]);
-      split2(qs[16 * j + 2 * t + 8], qs[16 * j + 2 * t + 9], qh[j][1], ql[j][1]);
-    } else {
-      qh[j][0] = qh[j][1] = ql[j][0] = ql[j][1] = 0u;
-    }
-  }
-  float m_run = -CUDART_INF_F, l_run = 0.f;
-  float o[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
-  int st = 0;
-  for (int blk = warp; blk < nblk; blk += kWarps, st ^= 1) {
-    if (blk + kWarps < nblk) {
-      fetch(blk + kWarps, st ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncwarp();
-    const uint32_t sk = (uint32_t)__cvta_generic_to_shared(&tile[warp][st][0][0]);
-    const uint32_t sv = (uint32_t)__cvta_generic_to_shared(&tile[warp][st][1][0]);
-    // ---- scores of 16 keys: two n-tiles of 8 keys, k = 64 head dims in 4 steps ----
-    float sc4[4];
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t bfr[4];
-        const int r = 8 * nt + (lane & 7), ch = 4 * half + (lane >> 3);
-        ldsm_x4(bfr, sk + (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4)));
-        mma16816(c, qh[2 * half][0], 0u, qh[2 * half][1], 0u, bfr[0], bfr[1]);
-        mma16816(c, ql[2 * half][0], 0u, ql[2 * half][1], 0u, bfr[0], bfr[1]);
-        mma16816(c, qh[2 * half + 1][0], 0u, qh[2 * half + 1][1], 0u, bfr[2], bfr[3]);
-        mma16816(c, ql[2 * half + 1][0], 0u, ql[2 * half + 1][1], 0u, bfr[2], bfr[3]);
-      }
-      const int k0 = blk * kBlk + 8 * nt + 2 * t;
-      sc4[2 * nt] = (k0 < nk) ? c[0] : -CUDART_INF_F;
-      sc4[2 * nt + 1] = (k0 + 1 < nk) ? c[1] : -CUDART_INF_F;
-    }
-    float bm = fmaxf(fmaxf(sc4[0], sc4[1]), fmaxf(sc4[2], sc4[3]));
-    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
-    bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
-    const float m_new = fmaxf(m_run, bm);
-    const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-    const float corr = (m_run == -CUDART_INF_F) ? 0.f : __expf(m_run - m_use);
-    float p[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) p[i] = (sc4[i] == -CUDART_INF_F) ? 0.f : __expf(sc4[i] - m_use);
-    l_run = l_run * corr + (p[0] + p[1]) + (p[2] + p[3]);
-    m_run = m_new;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      o[i][0] *= corr;
-      o[i][1] *= corr;
-      o[i][2] *= corr;
-      o[i][3] *= corr;
-    }
-    uint32_t ph[2], pl[2];
-    split2(p[0], p[1], ph[0], pl[0]);   // keys 2t, 2t+1     -> a0 (row g)
-    split2(p[2], p[3], ph[1], pl[1]);   // keys 8+2t, 9+2t   -> a2 (row g)
-    // ---- O (row 0) += P V: 8 n-tiles of 8 head dims, k = 16 keys; V^T fragments by ldmatrix.trans ----
-#pragma unroll
-    for (int dp = 0; dp < 4; ++dp) {
-      uint32_t bfr[4];
-      const int mtx = lane >> 3, r = (mtx & 1) * 8 + (lane & 7), ch = 2 * dp + (mtx >> 1);
-      ldsm_x4_t(bfr, sv + (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4)));
-      mma16816(o[2 * dp], ph[0], 0u, ph[1], 0u, bfr[0], bfr[1]);
-      mma16816(o[2 * dp], pl[0], 0u, pl[1], 0u, bfr[0], bfr[1]);
-      mma16816(o[2 * dp + 1], ph[0], 0u, ph[1], 0u, bfr[2], bfr[3]);
-      mma16816(o[2 * dp + 1], pl[0], 0u, pl[1], 0u, bfr[2], bfr[3]);
-    }
-    __syncwarp();   // the stage may be refilled by the next iteration's fetch
-  }
-  // ---- merge: 3 warps + the current token ----
-  {
-    float lt = l_run;
-    lt += __shfl_xor_sync(0xffffffffu, lt, 1);
-    lt += __shfl_xor_sync(0xffffffffu, lt, 2);
-    if (g == 0) {
-      if (t == 0) {
-        wm[warp] = m_run;
-        wl[warp] = lt;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        wo[warp][8 * i + 2 * t] = o[i][0];
-        wo[warp][8 * i + 2 * t + 1] = o[i][1];
-      }
-    }
-  }
-  const bool new_here = has_new && pos >= c0 && pos < c0 + n;
-  if (warp == 0) {
-    float dot = -CUDART_INF_F;
-    if (new_here) {
-      dot = qs[lane] * knew[lane] + qs[lane + 32] * knew[lane + 32];
-      dot = warp_sum(dot);
-    }
-    if (lane == 0) {
-      wm[kWarps] = dot;
-      wl[kWarps] = new_here ? 1.f : 0.f;
-    }
-    wo[kWarps][lane] = new_here ? vnew[lane] : 0.f;
-    wo[kWarps][lane + 32] = new_here ? vnew[lane + 32] : 0.f;
-  }
-  __syncthreads();
-  if (tid < HD) {
-    float mm = wm[0];
-#pragma unroll
-    for (int w = 1; w <= kWarps; ++w) mm = fmaxf(mm, wm[w]);
-    float lt = 0.f, ot = 0.f;
-#pragma unroll
-    for (int w = 0; w <= kWarps; ++w) {
-      if (wm[w] == -CUDART_INF_F) continue;
-      const float wgt = __expf(wm[w] - mm);
-      lt += wl[w] * wgt;
-      ot += wo[w][tid] * wgt;
-    }
-    if (nsplit == 1) {
-      const float r = lt > 0.f ? ot / lt : 0.f;
-      out[(int64_t)b * d + h * HD + tid] = r;
-      if (out16) out16[(int64_t)b * d + h * HD + tid] = __float2bfloat16_rn(r);
-    } else {
-      const int64_t pi = ((int64_t)b * n_head + h) * nsplit + sp;
-      part_o[pi * HD + tid] = ot;
-      if (tid == 0) {
-        part_ml[pi * 2] = n > 0 ? mm : -CUDART_INF_F;
-        part_ml[pi * 2 + 1] = n > 0 ? lt : 0.f;
-      }
-    }
-  }
-  vb_trace(TR_ATTN * 2 + 1);
-}
-
 __global__ void attn_decode_combine_kernel(const float *__restrict__ part_o,
                                            const float *__restrict__ part_ml, int n_head, int nsplit,
                                            float *__restrict__ out, bf16 *__restrict__ out16) {
@@ -974,10 +691,6 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
       VB_CUDA(launch_kernel(attn_decode_kernel<bf16>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
                             (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, finished, out,
                             (bf16 *)out16, part_o, part_ml, ns));
-  } else if (tune("VB_ATTN_DECODE_MMA", 1) != 0) {
-    VB_CUDA(launch_kernel(attn_decode_mma_kernel, grid, dim3(dmma::kThreads), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
-                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, finished, out,
-                          (bf16 *)out16, part_o, part_ml, ns));
   } else {
     // start of the region (percent of each stream) the kernel itself prefetches into L2 at launch; -1 = off.
     // The projection chain prefetches [0, VB_KV_PREFETCH_PCT) of the next launch's streams (api.cu)

@@ -277,7 +277,9 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
       vb_trace(TR_LN * 2);
       // ---- S1: LN1 + in-proj; q to scratch, k / v appended to the cache (activation.py:408) ----
       load_layernorm<NB>(P.x, B, d, LP.norm1_w, LP.norm1_b, xs, red);
+      if (l == 0) vb_trace(16);   // S1: LayerNorm done
       with_weights(g0 + 4 * l + 0, [&](const bf16 *wsm, int rows, int row0, int K) {
+        if (l == 0) vb_trace(18);  // S1: weight slot ready
         gemv_smem<NB>(wsm, rows, K, xs, [&](int r) { return LP.in_proj_b[row0 + r]; },
                       [&](int r, int b, float v, float bias) {
           if (b >= B) return;
@@ -291,7 +293,9 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
             (part == 1 ? kc : vc)[(int64_t)b * P.seq_stride + ((int64_t)h * P.cap + s_kvpos[b]) * HD + e] = __float2bfloat16_rn(v);
           }
         });
+        if (l == 0) vb_trace(20);  // S1: rows done
       });
+      if (l == 0) vb_trace(22);    // S1: next weights issued, about to arrive at the barrier
       grid_barrier(P.sync, target);
       // ---- S2: single-query attention, one (row, head, KV split) per CTA ----
       vb_trace(TR_ATTN * 2);
