@@ -233,7 +233,7 @@ def test_optimizer_step_changes_the_next_forward():
     g = load_golden("config0.pt")
     fw = g["forward"]
     m = build_model(g["config"], g["weight_seed"]).to(DEV).train()
-    opt = torch.optim.SGD(m.parameters(), lr=1e-2)
+    opt = torch.optim.SGD(m.parameters(), lr=2e-6)   # sum-reduced loss over ~800 target positions: large gradients
     losses = []
     for _ in range(3):
         m.rng = random.Random(0)

@@ -111,9 +111,15 @@ __device__ __forceinline__ int rows_per_cta(int N) { return (N + gridDim.x - 1) 
 template <int NB, typename Pre, typename Epi>
 __device__ __forceinline__ void gemv_smem(const bf16 *wsm, int rows, int K, const float *xs, Pre pre, Epi epi) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < rows; r += kWarps) {
+  constexpr int kMaxRows = 4;   // rows of one warp fetched up front (a CTA owns <= 32 rows of any matrix here)
+  decltype(pre(0)) cs[kMaxRows];
+#pragma unroll
+  for (int i = 0; i < kMaxRows; ++i)
+    if (warp + i * kWarps < rows) cs[i] = pre(warp + i * kWarps);
+  int ri = 0;
+  for (int r = warp; r < rows; r += kWarps, ++ri) {
     const bf16 *wr = wsm + (size_t)r * K;
-    const auto c = pre(r);
+    const auto c = ri < kMaxRows ? cs[ri < kMaxRows ? ri : 0] : pre(r);
     float acc[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = 0.f;
@@ -147,52 +153,47 @@ template <int NB> struct RowConst {   // bias of the row + the residual-stream v
   float res[NB];
 };
 
-// xs[b][:] = LayerNorm(x[b][:]) for the B rows (transformer.py:57-74); x read from L2 (written by other CTAs)
+// xs[b][:] = LayerNorm(x[b][:]) for the B rows (transformer.py:57-74); x read from L2 (written by other CTAs).
+// The row stays in registers (d <= 256 * 8); sum and sum of squares in ONE block reduction (two barriers in all).
 template <int NB>
 __device__ __forceinline__ void load_layernorm(const float *x, int B, int d, const float *gamma, const float *beta,
                                                float *xs, float *red) {
+  constexpr int MAXV = 8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float s[NB], q[NB];
+  float v[NB][MAXV];
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
-    s[b] = 0.f;
-    if (b < B)
-      for (int c = tid; c < d; c += kThreads) {
-        const float v = __ldcg(x + (int64_t)b * d + c);
-        xs[b * d + c] = v;
-        s[b] += v;
-      }
-    s[b] = warp_sum(s[b]);
-    if (lane == 0) red[b * kWarps + warp] = s[b];
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = tid + i * kThreads;
+      v[b][i] = (b < B && c < d) ? __ldcg(x + (int64_t)b * d + c) : 0.f;
+      s += v[b][i];
+      q += v[b][i] * v[b][i];
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) {
+      red[(2 * b) * kWarps + warp] = s;
+      red[(2 * b + 1) * kWarps + warp] = q;
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
-    float t = 0.f;
+    float s = 0.f, q = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += red[b * kWarps + w];
-    s[b] = t / (float)d;
-  }
-  __syncthreads();
+    for (int w = 0; w < kWarps; ++w) {
+      s += red[(2 * b) * kWarps + w];
+      q += red[(2 * b + 1) * kWarps + w];
+    }
+    const float mean = s / (float)d;
+    const float rstd = rsqrtf(fmaxf(q / (float)d - mean * mean, 0.f) + 1e-5f);
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    q[b] = 0.f;
-    if (b < B)
-      for (int c = tid; c < d; c += kThreads) {
-        const float t = xs[b * d + c] - s[b];
-        q[b] += t * t;
-      }
-    q[b] = warp_sum(q[b]);
-    if (lane == 0) red[b * kWarps + warp] = q[b];
-  }
-  __syncthreads();
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += red[b * kWarps + w];
-    const float rstd = rsqrtf(t / (float)d + 1e-5f);
-    for (int c = tid; c < d; c += kThreads) xs[b * d + c] = b < B ? (xs[b * d + c] - s[b]) * rstd * gamma[c] + beta[c] : 0.f;
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = tid + i * kThreads;
+      if (c < d) xs[b * d + c] = b < B ? (v[b][i] - mean) * rstd * gamma[c] + beta[c] : 0.f;
+    }
   }
   __syncthreads();
 }
@@ -212,8 +213,8 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
   bf16 *wbuf[2] = {reinterpret_cast<bf16 *>(smem_raw), reinterpret_cast<bf16 *>(smem_raw + P.wbuf_bytes)};
   float *xs = reinterpret_cast<float *>(smem_raw + 2 * (size_t)P.wbuf_bytes);   // [NB][max(d, dff)]
   float *sc = xs + (size_t)NB * max(d, dff);                                     // [kMaxChunk] scores / [32][65] reduce
-  float *red = sc + kMaxChunk + 64;                                              // [0,32) reductions, [32,96) query
-  uint64_t *wbar = reinterpret_cast<uint64_t *>(red + 128);                      // [2]
+  float *red = sc + kMaxChunk + 64;                                              // [0,64) reductions, [64,128) query
+  uint64_t *wbar = reinterpret_cast<uint64_t *>(red + 128);  // (red: 128 floats)                      // [2]
   __shared__ int s_all_done, s_tok, s_pos;
   __shared__ int s_kvpos[4], s_fin[4];   // per step: cache row of the current token, stop flag of every batch row
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
           const int c0 = sp * chunk, n = max(0, min(kv_len, c0 + chunk) - c0);
           const bf16 *kb = kc + (int64_t)b * P.seq_stride + (int64_t)h * P.cap * HD;
           const bf16 *vb_ = vc + (int64_t)b * P.seq_stride + (int64_t)h * P.cap * HD;
-          float *qs = red + 32;   // [64] staged query
+          float *qs = red + 64;   // [64] staged query
           const int g8 = lane >> 3, j8 = (lane & 7) * 8;
           const int eg = (tid & 7) * 8, jl = tid >> 3;
           // the first 128 keys' K and V rows and the query in ONE L2 / HBM round trip (the cache rows do not depend on q)
@@ -553,7 +554,8 @@ __global__ void __launch_bounds__(kThreads, 1) ar_steps_small_kernel(const __gri
 }  // namespace sm
 
 bool decode_small_supported(const vb_decoder_desc &D, int B, int cache_cap) {
-  if (D.wdtype != VB_BF16 || B < 1 || B > 4 || D.n_layer > sm::kMaxLayers || D.d_model % 256 != 0 || D.d_ff % 256 != 0)
+  if (D.wdtype != VB_BF16 || B < 1 || B > 4 || D.n_layer > sm::kMaxLayers || D.d_model % 256 != 0 || D.d_ff % 256 != 0 ||
+      D.d_model > 2048)
     return false;
   if (tune("VB_DECODE_SMALL", 1) == 0) return false;
   const int G = sm_count();
