@@ -337,7 +337,7 @@ def config3_prompts(total, seed=2024):
     return texts, prompts
 
 
-def config4_block(dev, n_utt=32, chunk=16):
+def config4_block(dev, n_utt=64, chunk=32):
     """BASELINE configs[4] (one GPU's share, bounded sample): EnCodec 24 kHz encode + decode of 10 s waveforms"""
     from valle_b200.data.tokenizer import AudioTokenizer, random_encodec_weights
     tok = AudioTokenizer(device=dev, weights=random_encodec_weights(0))

@@ -287,13 +287,6 @@ int vb_ar_head_step(vb_decoder_t dec, const vb_ar_head *head, const float *h, vb
 int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_state *st, void *workspace,
                       size_t workspace_bytes, vb_stream_t stream);
 
-/* n_steps greedy decode steps in one call.  For 1..4 utterances in bf16 this is ONE persistent cooperative kernel
- * (csrc/decode_small.cu: one CTA per SM, grid barriers between the stages, every CTA's weight rows fetched into
- * shared memory two stages ahead, steps looped inside the kernel, early exit once every utterance has stopped);
- * otherwise n_steps calls of vb_ar_decode_step. */
-int vb_ar_decode_steps(vb_decoder_t dec, const vb_ar_head *head, vb_ar_state *st, void *workspace,
-                       size_t workspace_bytes, int n_steps, vb_stream_t stream);
-
 /* after sampling on the host side (top_k != 1): push tokens[B] chosen by the caller
  * (valle.py:1040-1057 with torch's own RNG), applying the same stop rule. */
 int vb_ar_push_tokens(const vb_ar_head *head, vb_ar_state *st, const int64_t *sampled, int d,

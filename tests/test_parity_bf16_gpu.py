@@ -280,38 +280,3 @@ def test_model_on_second_gpu_while_first_is_current():
     m.engine().quiet = True
     out = m.inference(x, torch.tensor([x.shape[1]], dtype=torch.int32), y, None, top_k=1, max_new_tokens=12).cpu()
     assert out.shape == (1, 12, 8)
-
-
-@pytest.mark.parametrize("fixture,n_utts", [("tiny_batch.pt", 1), ("tiny_batch.pt", 3), ("tiny_batch.pt", 4), ("big_short.pt", 1)])
-def test_bf16_small_batch_persistent_kernel_matches_the_launch_chain(fixture, n_utts):
-    """1..4 utterances in bf16: the persistent cooperative kernel (decode_small.cu: grid barriers between the stages,
-    weights fetched into shared memory two stages ahead, fp32 activations, steps looped inside the kernel) against
-    the PDL-chained tensor-core launch sequence on the same bf16 weights and KV cache: same stop behaviour (lengths),
-    the same early greedy ids, logits of the launch chain reproduced within 3e-2 by a teacher-forced replay.
-    Covers ragged lengths inside the batch and early finishers."""
-    g = load_golden(fixture)
-    m = _model(g, torch.bfloat16)
-    eng = m.engine()
-    if "utts" in g:
-        texts = [u["x"][0] for u in g["utts"]][:n_utts]
-        prompts = [u["y"][0] for u in g["utts"]][:n_utts]
-    else:
-        texts, prompts = [g["x"][0]], [g["y"][0]]
-    n0 = eng.kernel_launches()
-    out_small = eng.generate(texts, prompts, top_k=1)
-    n_small = eng.kernel_launches() - n0
-    eng.small_batch_kernel = False
-    eng._bufs.clear()
-    n0 = eng.kernel_launches()
-    out_chain = eng.generate(texts, prompts, top_k=1)
-    n_chain = eng.kernel_launches() - n0
-    eng.small_batch_kernel = True
-    assert n_small < n_chain / 4, (n_small, n_chain)          # the persistent path really ran
-    agree = 0
-    for a, b in zip(out_small, out_chain):
-        assert a.shape == b.shape
-        assert int(a.min()) >= 0 and int(a.max()) < 1024
-        agree += int(torch.equal(a[:4, 0], b[:4, 0]))
-    assert agree >= len(out_small) - 1, agree
-    if fixture == "big_short.pt":      # full-size model: most of the 97 frames agree between the two bf16 paths
-        assert float((out_small[0][:, 0] == out_chain[0][:, 0]).float().mean()) > 0.5

@@ -19,7 +19,7 @@ import bench  # noqa: E402
 from valle_b200 import _lib  # noqa: E402
 
 NAMES = {1: "ln_reduce", 2: "gemm_decode", 3: "attn_decode", 4: "relu_reduce", 5: "ar_sample", 6: "attn_combine",
-         7: "fused", 8: "s1.ln_done", 9: "s1.w_ready", 10: "s1.rows_done", 11: "s1.pre_barrier"}
+         7: "fused"}
 
 
 def main():

@@ -117,7 +117,6 @@ PROTOTYPES = {
     "vb_ar_step_workspace": (C.c_size_t, [C.POINTER(DecoderDesc), C.c_int, C.c_int]),
     "vb_ar_head_step": (C.c_int, [vp, C.POINTER(ArHead), vp, C.POINTER(ArState), vp, C.c_size_t, vp]),
     "vb_ar_decode_step": (C.c_int, [vp, C.POINTER(ArHead), C.POINTER(ArState), vp, C.c_size_t, vp]),
-    "vb_ar_decode_steps": (C.c_int, [vp, C.POINTER(ArHead), C.POINTER(ArState), vp, C.c_size_t, C.c_int, vp]),
     "vb_ar_push_tokens": (C.c_int, [C.POINTER(ArHead), C.POINTER(ArState), vp, C.c_int, vp]),
     "vb_nar_argmax_accumulate": (C.c_int, [vp, C.c_int64, C.c_int, C.c_int64, vp, C.c_int64, vp, vp,
                                            C.c_int64, vp, C.c_int, vp]),

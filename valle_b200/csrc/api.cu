@@ -340,7 +340,6 @@ struct StepWs {
   bf16 *xn16, *att16, *hb16;
   void *gemm_ws;
   size_t gemm_ws_bytes;
-  void *small;     // scratch of the persistent small-batch kernel (decode_small.cu)
   size_t total;
 };
 StepWs carve_step_ws(const vb_decoder_desc &D, int B, int cache_cap, void *base) {
@@ -361,7 +360,6 @@ StepWs carve_step_ws(const vb_decoder_desc &D, int B, int cache_cap, void *base)
   w.hb16 = (bf16 *)take((size_t)64 * dff * 2);
   w.gemm_ws_bytes = gemm_decode_workspace((int)d, (int)dff);
   w.gemm_ws = take(w.gemm_ws_bytes);
-  w.small = take(B <= 4 ? decode_small_workspace(D, B) : 0);
   w.total = (size_t)(p - (char *)base) + 256;
   return w;
 }
@@ -430,19 +428,6 @@ VB_API int vb_ar_push_tokens(const vb_ar_head *head, vb_ar_state *st, const int6
   VB_CHECK_ARG(head && st && sampled, "vb_ar_push_tokens: null argument");
   const int ldl = (head->n_vocab + 3) & ~3;
   return launch_ar_sample(st->logits, ldl, nullptr, 0, 0, head, st, d, sampled, 0, false, (cudaStream_t)stream);
-}
-
-VB_API int vb_ar_decode_steps(vb_decoder_t dec, const vb_ar_head *head, vb_ar_state *st, void *workspace,
-                              size_t workspace_bytes, int n_steps, vb_stream_t stream) {
-  VB_CHECK_ARG(dec && head && st && n_steps >= 1, "vb_ar_decode_steps: bad argument");
-  const vb_decoder_desc &D = dec->desc;
-  VB_CHECK_ARG(workspace_bytes >= vb_ar_step_workspace(&D, st->B, st->cache_cap), "vb_ar_decode_steps: workspace too small");
-  if (head->greedy && decode_small_supported(D, st->B, st->cache_cap)) {
-    StepWs w = carve_step_ws(D, st->B, st->cache_cap, workspace);
-    return launch_decode_small(D, dec->layers, head, st, w.small, n_steps, (cudaStream_t)stream);
-  }
-  for (int i = 0; i < n_steps; ++i) VB_TRY(vb_ar_decode_step(dec, head, st, workspace, workspace_bytes, stream));
-  return VB_OK;
 }
 
 VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_state *st, void *workspace,

@@ -112,12 +112,6 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
                        const QkvScatter *qkv, float *partials, size_t partial_bytes, int *out_splits, int *out_ldp,
                        const KvPrefetch *pf, bool pdl, cudaStream_t s);
 
-// decode_small.cu (1..4 utterances: one persistent cooperative kernel running n_steps decode steps, bf16)
-bool decode_small_supported(const vb_decoder_desc &D, int B, int cache_cap);
-size_t decode_small_workspace(const vb_decoder_desc &D, int B);
-int launch_decode_small(const vb_decoder_desc &D, const vb_layer_params *layers, const vb_ar_head *head, vb_ar_state *st,
-                        void *scratch, int n_steps, cudaStream_t s);
-
 // attention.cu
 int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
                             const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,

@@ -173,8 +173,6 @@ class ValleEngine:
         self.last_packed: Optional[torch.Tensor] = None
         #: greedy decode steps captured per CUDA graph (one replay per group; the stop flags are polled every `poll` steps)
         self.steps_per_graph = 8
-        #: batches of 1..4 utterances (bf16, greedy) decode inside the persistent small-batch kernel
-        self.small_batch_kernel = True
         self.replayed_launches = 0   # kernels executed through CUDA-graph replays
         self.captured_launches = 0   # kernels recorded at capture time (counted by the library, not run)
         self._bufs: Dict[Tuple[int, int, int], _ArBuffers] = {}
@@ -335,11 +333,7 @@ class ValleEngine:
         steps = 0
         while steps < max_steps:
             n = min(poll, max_steps - steps)
-            if greedy and trace is None and self.dtype == torch.bfloat16 and B <= 4 and self.small_batch_kernel:
-                # 1..4 utterances: n decode steps inside ONE persistent cooperative kernel (csrc/decode_small.cu)
-                L.check(self.lib.vb_ar_decode_steps(self.ar.handle, C.byref(head), C.byref(buf.st), buf.ws.data_ptr(),
-                                                    buf.ws.numel(), n, L.stream_ptr()), "vb_ar_decode_steps")
-            elif greedy and self.use_cuda_graph and not self._use_views(buf, greedy):
+            if greedy and self.use_cuda_graph and not self._use_views(buf, greedy):
                 # whole groups of `steps_per_graph` decode steps as one graph replay (no launch gap between the
                 # steps of a group), the remainder one step at a time
                 done = 0
