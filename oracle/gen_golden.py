@@ -207,6 +207,40 @@ def gen_topk(ref):
                               weight_seed=seed, checksums=checksums(m.state_dict()), x=x, y=y, cases=cases))
 
 
+def gen_switches(ref):
+    """the constructor switches beyond the north-star configuration that the engine builds: prepend_bos (valle.py:
+    1006-1007,1059-1065,329-332) and nar_scale_factor != 1 (valle.py:83,231-247): greedy inference codes and the
+    training losses of a small padded batch, from the unmodified reference"""
+    import random
+    for name, d, h, l, bos, f in (("tiny_bos", 256, 4, 2, True, 1.0), ("tiny_scale", 512, 8, 2, False, 0.5)):
+        torch.manual_seed(0)
+        m = ref.VALLE(d, h, l, norm_first=True, add_prenet=False, prefix_mode=1, share_embedding=True,
+                      nar_scale_factor=f, prepend_bos=bos, num_quantizers=8).eval()
+        g = torch.Generator().manual_seed(31)
+        x, y = make_inputs(g, 6, 14)
+        xl = torch.tensor([x.shape[1]], dtype=torch.int32)
+        with torch.no_grad():
+            codes = m.inference(x, xl, y, None, top_k=1)
+        N = 3
+        xx = torch.randint(3, 100, (N, 12), generator=g)
+        xls = torch.tensor([12, 9, 7], dtype=torch.int32)
+        yy = torch.randint(0, 1024, (N, 40, 8), generator=g)
+        yls = torch.tensor([40, 31, 22], dtype=torch.int32)
+        fw = {}
+        for stage in (0, 1, 2):
+            m.rng = random.Random(0)
+            torch.manual_seed(5)
+            with torch.no_grad():
+                (_, _), loss, _ = m(xx, xls, yy, yls, train_stage=stage)
+            fw[f"loss_stage{stage}"] = torch.as_tensor(float(loss))
+        fw.update(x=xx, x_lens=xls, y=yy.to(torch.int16), y_lens=yls, torch_seed=5)
+        print(f"{name}: frames={codes.shape[1]} losses={[float(fw[f'loss_stage{s}']) for s in (0, 1, 2)]}")
+        save(f"{name}.pt", dict(config=dict(d_model=d, nhead=h, num_layers=l, prefix_mode=1, num_quantizers=8,
+                                            prepend_bos=bos, nar_scale_factor=f),
+                                weight_seed=0, checksums=checksums(m.state_dict()), x=x, y=y,
+                                codes=codes.to(torch.int16), forward=fw))
+
+
 def main(argv):
     ref = load_reference()
     what = argv or ["tiny", "batch", "config0", "big_short"]
@@ -219,6 +253,8 @@ def main(argv):
         gen_config0(ref)
     if "big_short" in what:
         gen_big(ref, 6, 30, "big_short")
+    if "switches" in what:
+        gen_switches(ref)
     if "topk" in what:
         gen_topk(ref)
     if "big_full" in what:

@@ -280,3 +280,19 @@ def test_model_on_second_gpu_while_first_is_current():
     m.engine().quiet = True
     out = m.inference(x, torch.tensor([x.shape[1]], dtype=torch.int32), y, None, top_k=1, max_new_tokens=12).cpu()
     assert out.shape == (1, 12, 8)
+
+
+def test_bf16_batches_above_64_are_decoded_in_tensor_core_groups():
+    """B = 70 > 64 (one UMMA N tile): the engine decodes groups of <= 64 rows on the tensor-core chain instead of
+    dropping onto the CUDA-core GEMV path; every utterance equals its decode inside a batch of <= 64."""
+    g = load_golden("tiny_batch.pt")
+    m = _model(g, torch.bfloat16)
+    eng = m.engine()
+    texts = ([u["x"][0] for u in g["utts"]] * 18)[:70]
+    prompts = ([u["y"][0] for u in g["utts"]] * 18)[:70]
+    n0 = eng.kernel_launches()
+    out = eng.generate(texts, prompts, top_k=1, max_new_tokens=12, return_device=True)
+    assert len(out) == 70 and eng.last_packed.shape == (70 * 12, 8)
+    ref = eng.generate(texts[:4], prompts[:4], top_k=1, max_new_tokens=12)
+    for i in range(70):
+        assert torch.equal(out[i].cpu(), ref[i % 4]), i

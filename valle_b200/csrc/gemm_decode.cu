@@ -226,7 +226,7 @@ size_t gemm_decode_workspace(int d_model, int d_ff) {
 static int pick_splits(int tiles, int num_kb) {
   int s = sm_count() / tiles;
   s = max(1, min(s, num_kb / 2));
-  return max(1, min(s, 32));
+  return max(1, min(s, kMaxForcedSplits));   // the consumers keep up to kMaxForcedSplits slabs of a column in flight
 }
 
 int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, int N, int K, int force_splits,

@@ -159,6 +159,10 @@ class ValleEngine:
             raise L.VbError("valle_b200: move the model to a CUDA device first (no CPU fallback)")
         self.device = p.device
         self.d = p.shape[1]
+        #: width of the NAR stack (valle.py:83: nar_d_model = d_model * nar_scale_factor)
+        self.d_nar = model.nar_audio_embeddings[0].weight.shape[1] if model.num_quantizers > 1 else self.d
+        #: AR sequences start with <BOS> (id 1025) ahead of the acoustic prompt (valle.py:1006-1007)
+        self.prepend_bos = bool(getattr(model, "ar_audio_prepend_bos", False))
         self.n_vocab = p.shape[0]
         self.Q = model.num_quantizers
         self.prefix_mode = model.prefix_mode
@@ -171,6 +175,8 @@ class ValleEngine:
         #: micro-batches decoded concurrently on separate streams when B >= 32 (bf16 tensor-core path)
         self.micro_batches = 1
         self.last_packed: Optional[torch.Tensor] = None
+        #: rows of one tensor-core decode group (gemm_decode.cu: one UMMA N tile); larger bf16 batches are split
+        self.max_tc_batch = 64
         #: greedy decode steps captured per CUDA graph (one replay per group; the stop flags are polled every `poll` steps)
         self.steps_per_graph = 8
         self.replayed_launches = 0   # kernels executed through CUDA-graph replays
@@ -247,6 +253,24 @@ class ValleEngine:
         m, dev, d, Q = self.model, self.device, self.d, self.Q
         B = len(texts)
         assert B == len(prompts) and B >= 1
+        if B > self.max_tc_batch and self.dtype == torch.bfloat16 and trace is None and forced is None:
+            # the tensor-core decode projections take up to 64 rows (one UMMA N tile): a larger batch is decoded as
+            # consecutive groups of <= 64 utterances instead of falling onto the CUDA-core GEMV path
+            outs: List[torch.Tensor] = []
+            stats = EngineStats()
+            packed = []
+            for b0 in range(0, B, self.max_tc_batch):
+                b1 = min(B, b0 + self.max_tc_batch)
+                outs += self.generate(texts[b0:b1], prompts[b0:b1], None if enroll_lens is None else enroll_lens[b0:b1],
+                                      top_k, temperature, max_new_tokens, poll, return_device, None, None)
+                stats.ar_steps += self.stats.ar_steps
+                stats.ar_ms += self.stats.ar_ms
+                stats.prefill_ms += self.stats.prefill_ms
+                stats.nar_ms += self.stats.nar_ms
+                packed.append(self.last_packed)
+            self.stats = stats
+            self.last_packed = torch.cat(packed) if return_device else None
+            return outs
         S = [int(t.numel()) for t in texts]
         Tp = [int(p.shape[0]) for p in prompts]
         assert all(s > 0 for s in S) and all(p.shape[1] == Q for p in prompts)
@@ -254,6 +278,9 @@ class ValleEngine:
         _check_ids([p[:, :1] for p in prompts], NUM_AUDIO_TOKENS + 1, "prompt code (first codebook)")  # 1025-row tables
         _check_ids([p[:, 1:] for p in prompts], NUM_AUDIO_TOKENS, "prompt code")
         cap_new = [16 * s for s in S]  # valle.py:1047: stop when n_new > 16 * S
+        if self.prepend_bos:
+            # y carries the <BOS> the prompt does not: (y.shape[1] - prompts.shape[1]) = n_new + 1 (valle.py:1045-1047)
+            cap_new = [c - 1 for c in cap_new]
         if max_new_tokens is not None:
             cap_new = [min(c, max_new_tokens - 1) for c in cap_new]
         tok_stride = (max(cap_new) + 2 + 7) // 8 * 8
@@ -271,6 +298,11 @@ class ValleEngine:
         # ---- host -> device (once per batch) ----
         text_all = torch.cat([t.reshape(-1).to(torch.int64) for t in texts]).to(dev, non_blocking=True)
         prm_all = torch.cat([p.to(torch.int64) for p in prompts]).contiguous().to(dev, non_blocking=True)
+        Tp_nar = Tp
+        if self.prepend_bos:   # the AR stack sees [<BOS> | first-codebook prompt]; the NAR stages see the prompt only
+            bos = torch.full((1,), NUM_AUDIO_TOKENS + 1, dtype=torch.int64)
+            ar_tok = torch.cat([torch.cat([bos, p[:, 0].to(torch.int64).cpu()]) for p in prompts]).to(dev, non_blocking=True)
+            Tp = [t + 1 for t in Tp]
         seq_len = [S[b] + Tp[b] for b in range(B)]
         cu = [0]
         for n in seq_len:
@@ -305,7 +337,10 @@ class ValleEngine:
         pe_a = self._pe(m.ar_audio_position, max(Tp) + max(cap_new) + 2)
         x = torch.empty((M, d), dtype=torch.float32, device=dev)
         self._embed_pe(text_all, 1, m.ar_text_embedding.weight, pe_t, m.ar_text_position.alpha, sum(S), x, trow_d, tpos_d)
-        self._embed_pe(prm_all, Q, m.ar_audio_embedding.weight, pe_a, m.ar_audio_position.alpha, sum(Tp), x, arow_d, apos_d)
+        if self.prepend_bos:
+            self._embed_pe(ar_tok, 1, m.ar_audio_embedding.weight, pe_a, m.ar_audio_position.alpha, sum(Tp), x, arow_d, apos_d)
+        else:
+            self._embed_pe(prm_all, Q, m.ar_audio_embedding.weight, pe_a, m.ar_audio_position.alpha, sum(Tp), x, arow_d, apos_d)
         self.ar.forward(x, cu_d, B, max(seq_len), L.VB_MASK_VALLE_AR, S_d, None, buf.kcache, buf.vcache, cap)
         h_last = ops.gather_rows(x, last_d)
         head = self._head(pe_a, greedy)
@@ -361,7 +396,7 @@ class ValleEngine:
             raise SyntaxError("well trained model shouldn't reach here.")  # valle.py:1049-1052
         if not self.quiet:
             for b in range(B):
-                print(f"VALL-E EOS [{Tp[b]} -> {Tp[b] + n_gen[b]}]")  # valle.py:1054
+                print(f"VALL-E EOS [{Tp_nar[b]} -> {Tp[b] + n_gen[b]}]")  # valle.py:1054
 
         # ---- NAR (valle.py:1059-1137) ----
         Tg = n_gen
@@ -376,7 +411,7 @@ class ValleEngine:
             fc = None
             if forced is not None:
                 fc = torch.cat([forced[b][: Tg[b]].to(torch.int64) for b in range(B)]).to(dev)
-            self._nar(texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, enroll_lens, forced_codes=fc,
+            self._nar(texts, text_all, prm_all, S, Tp_nar, Tg, cu_g, codes, enroll_lens, forced_codes=fc,
                       trace=trace if (trace is not None and trace.get("nar")) else None)
         ev[3].record()
         ev[3].synchronize()
@@ -428,7 +463,7 @@ class ValleEngine:
     def _embed_pe(self, tokens, tok_stride, table, pe, alpha, n, x, rows, pos):
         """x[rows[r]] = table[tokens[r*tok_stride]] + alpha * pe[pos[r]]  (embedding then position,
         valle.py:995-997 / 1013-1015)."""
-        tmp = torch.empty((n, self.d), dtype=torch.float32, device=self.device)
+        tmp = torch.empty((n, table.shape[1]), dtype=torch.float32, device=self.device)
         ops.embed_sum(tokens, tok_stride, 0, [table.detach()], n, tmp)
         ops.add_pe(tmp, pe, alpha.detach(), x, n, positions=pos, out_rows=rows)
 
@@ -537,7 +572,7 @@ class ValleEngine:
 
     def _nar(self, texts, text_all, prm_all, S, Tp, Tg, cu_g, codes, enroll_lens, trim_text: bool = True,
              forced_codes: Optional[torch.Tensor] = None, trace: Optional[dict] = None):
-        m, dev, d, Q = self.model, self.device, self.d, self.Q
+        m, dev, d, Q = self.model, self.device, self.d_nar, self.Q
         B = len(S)
         pm = self.prefix_mode
         # text seen by the NAR decoder (valle.py:1068-1079)

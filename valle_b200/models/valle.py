@@ -77,12 +77,13 @@ class VALLE(nn.Module):
         super().__init__()
         prepend_bos = bool(kwargs.pop("prepend_bos", False))
         num_quantizers = int(kwargs.pop("num_quantizers", 8))
-        if add_prenet or prepend_bos or nar_scale_factor != 1.0 or not norm_first:
+        if add_prenet or not norm_first:
             raise NotImplementedError(
-                "valle_b200.VALLE builds the north-star configuration (norm_first=True, add_prenet=False, "
-                "prepend_bos=False, nar_scale_factor=1.0); the other reference switches are listed as "
-                "'next' in DESIGN.md")
+                "valle_b200.VALLE: add_prenet=True (conv / linear pre-nets, valle.py:96-131,181-214) and post-LN "
+                "(norm_first=False) are not built; prepend_bos and nar_scale_factor are (DESIGN.md section 7)")
         nar_d_model = int(d_model * nar_scale_factor)
+        if nar_d_model % 256 != 0 or nar_d_model // max(1, int(nhead * nar_scale_factor)) != 64:
+            raise NotImplementedError("valle_b200.VALLE: nar_scale_factor must keep d_model a multiple of 256 and 64-wide heads")
         # creation order == valle.py:85-259 so that a fixed torch seed yields the reference's weights
         self.ar_text_embedding = TokenEmbedding(d_model, NUM_TEXT_TOKENS)
         self.nar_text_embedding = TokenEmbedding(nar_d_model, NUM_TEXT_TOKENS)
@@ -150,8 +151,11 @@ class VALLE(nn.Module):
                     yield pair
 
     def pad_y_eos(self, y, y_mask_int, eos_id):
-        """append EOS after the last valid frame and split into (input, target), valle.py:322-333"""
+        """append EOS after the last valid frame and split into (input, target), valle.py:322-333; with prepend_bos the
+        inputs are [BOS, y...] and the targets keep every position (:329-332)"""
         targets = F.pad(y, (0, 1), value=0) + eos_id * F.pad(y_mask_int, (0, 1), value=1)
+        if self.ar_audio_prepend_bos:
+            return F.pad(targets[:, :-1], (1, 0), value=NUM_AUDIO_TOKENS + 1), targets
         return targets[:, :-1], targets[:, 1:]
 
     # ---- engine -------------------------------------------------------------------------------

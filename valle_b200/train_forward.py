@@ -65,6 +65,15 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
     if dev.type != "cuda":
         raise L.VbError("valle_b200: the model must live on a CUDA device (no CPU fallback)")
     dtype = model.engine_dtype
+    if torch.is_autocast_enabled():
+        # bin/trainer.py:525 wraps the call in torch.cuda.amp.autocast(dtype=...): reduced-precision autocast selects
+        # the tensor-core (bf16 storage, fp32 accumulate) path; fp16 autocast is served by the same bf16 kernels
+        try:
+            ac = torch.get_autocast_dtype("cuda")
+        except Exception:
+            ac = torch.get_autocast_gpu_dtype()
+        if ac in (torch.bfloat16, torch.float16):
+            dtype = torch.bfloat16
     x, y = x.to(dev), y.to(dev)
     x_lens, y_lens = x_lens.to(dev), y_lens.to(dev)
     N, d, Q = x.shape[0], model.ar_predict_layer.weight.shape[1], model.num_quantizers
@@ -84,7 +93,7 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
         """[N, T] ids -> [N, T, d] = table[ids] + alpha * pe[:T]."""
         tok = tokens.reshape(-1).contiguous()
         e = AG.EmbedSum.apply(tok, 1, 0, tok.numel(), table)
-        return add_pe(e.view(N, T, d), pos_mod, T)
+        return add_pe(e.view(N, T, table.shape[1]), pos_mod, T)
 
     def add_pe(e, pos_mod, T):
         return AG.AddPe.apply(e, pos_mod.table(T, dev), pos_mod.alpha)
@@ -115,12 +124,14 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
     # ---- AR decoder (valle.py:828-881) ----
     if train_stage in (0, 1):
         xe = embed_pe(text, model.ar_text_embedding.weight, model.ar_text_position, Smax)
-        ye = embed_pe(yin.contiguous(), model.ar_audio_embedding.weight, model.ar_audio_position, Tmax)
-        rows = torch.cat([xe, ye], dim=1).reshape(N * (Smax + Tmax), d).contiguous()
+        Ta = yin.shape[1]                     # Tmax, or Tmax + 1 with the prepended <BOS> (valle.py:820-826,833)
+        ye = embed_pe(yin.contiguous(), model.ar_audio_embedding.weight, model.ar_audio_position, Ta)
+        rows = torch.cat([xe, ye], dim=1).reshape(N * (Smax + Ta), d).contiguous()
         nd = model.ar_decoder.native(dtype)
-        rows = stack(model.ar_decoder, nd, rows, yl32, L.VB_MASK_PADDED_AR, None, Smax + Tmax)
-        sel = (torch.arange(N, device=dev)[:, None] * (Smax + Tmax) + Smax
-               + torch.arange(Tmax, device=dev)[None, :]).reshape(-1).to(torch.int32).contiguous()
+        yl_ar = (yl32 + (Ta - Tmax)).contiguous()
+        rows = stack(model.ar_decoder, nd, rows, yl_ar, L.VB_MASK_PADDED_AR, None, Smax + Ta)
+        sel = (torch.arange(N, device=dev)[:, None] * (Smax + Ta) + Smax
+               + torch.arange(Ta, device=dev)[None, :]).reshape(-1).to(torch.int32).contiguous()
         hn = final_norm(nd, rows, None, sel)
         logits = AG.Linear.apply(hn, model.ar_predict_layer.weight, dtype)
         tg = targets.reshape(-1).contiguous()
@@ -142,7 +153,7 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
 
         def emb_sum(tok2d, tabs, T):  # [N, T, len(tabs)] ids -> sum_j tabs[j][ids[..., j]] in order
             tok = tok2d.reshape(-1, len(tabs)).contiguous()
-            return AG.EmbedSum.apply(tok, len(tabs), 1, tok.shape[0], *tabs).view(N, T, d)
+            return AG.EmbedSum.apply(tok, len(tabs), 1, tok.shape[0], *tabs).view(N, T, tabs[0].shape[1])
 
         if pm == 0:  # valle.py:339-345
             prefix_len = 0
@@ -180,7 +191,7 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
             tg = tg[:, prefix_len:]
         y_pos = add_pe(y_emb.contiguous(), model.nar_audio_position, Ty)
         Lp = Smax + Ty
-        rows = torch.cat([xe, y_pos], dim=1).reshape(N * Lp, d).contiguous()
+        rows = torch.cat([xe, y_pos], dim=1).reshape(N * Lp, xe.shape[-1]).contiguous()
         nd = model.nar_decoder.native(dtype)
         ada = ada_table(model.nar_decoder, nd, model.nar_stage_embeddings[nar_stage - 1].weight)
         rows = stack(model.nar_decoder, nd, rows, seg1, L.VB_MASK_PADDED, ada, Lp)
