@@ -43,17 +43,13 @@ ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *
       v[i] = *reinterpret_cast<const float4 *>(xr + c);
       if (partials) {
         const float *p = partials + (int64_t)b * ldp + c;
-        // every slab of this column in flight at once (one L2 round trip), summed in fixed order 0..S-1
-        float4 t[kMaxForcedSplits];
-#pragma unroll
-        for (int sidx = 0; sidx < kMaxForcedSplits; ++sidx)
-          if (sidx < splits) t[sidx] = __ldcg(reinterpret_cast<const float4 *>(p + (int64_t)sidx * 64 * ldp));
-        float4 a = t[0];
-#pragma unroll
-        for (int sidx = 1; sidx < kMaxForcedSplits; ++sidx)
-          if (sidx < splits) {
-            a.x += t[sidx].x; a.y += t[sidx].y; a.z += t[sidx].z; a.w += t[sidx].w;
-          }
+        // (keeping all <= 16 slabs of the column in flight at once measured slower: 3.93 vs 3.7 us per launch)
+        float4 a = __ldcg(reinterpret_cast<const float4 *>(p));
+#pragma unroll 6
+        for (int sidx = 1; sidx < splits; ++sidx) {
+          const float4 t = __ldcg(reinterpret_cast<const float4 *>(p + (int64_t)sidx * 64 * ldp));
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+        }
         if (bias) {
           a.x += bb[i].x; a.y += bb[i].y; a.z += bb[i].z; a.w += bb[i].w;
         }
