@@ -31,7 +31,7 @@ for rep in range(2):
             lib.vb_tune_set(k.encode(), touched[k])
         kv = dict(x.split("=") for x in c.split(",") if x)
         for k, v in kv.items():
-            touched.setdefault(k, {"VB_KV_PREFETCH_PCT": 40, "VB_ATTN_PF_K_FROM": -1, "VB_ATTN_PF_V_FROM": -1}.get(k, 0))
+            touched.setdefault(k, {"VB_KV_PREFETCH_PCT": 40}.get(k, 0))
             lib.vb_tune_set(k.encode(), int(v))
         eng._bufs.clear()
         eng.generate(texts, prompts, top_k=1, max_new_tokens=min(40, frames), return_device=True)   # capture

@@ -451,8 +451,6 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
     // beat 20 / 60 %.
     const int pf_env = tune("VB_KV_PREFETCH_PCT", 40);
     const int pf_pct = B >= 16 ? pf_env : 0;
-    const int pf_bulk = tune("VB_KV_PF_BULK", 0);
-    const int pf_by_row = tune("VB_KV_PF_BY_ROW", 0);
     const int qkv_env = tune("VB_SPLITS_QKV", 0);
     const int out_splits = tune("VB_SPLITS_OUT", 0);   // 0 = fill the SMs
     const int ffn1_env = tune("VB_SPLITS_FFN1", 0);
@@ -473,17 +471,7 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
       pf.seq_stride_bytes = (int64_t)st->cache_seq_stride * (int64_t)ts;
       pf.B = B; pf.H = D.n_head; pf.cap = st->cache_cap; pf.row_bytes = (int)(hd * ts);
       pf.text_len = st->text_len; pf.prompt_len = st->prompt_len; pf.n_gen = st->n_gen;
-      pf.bulk = pf_bulk;
-      if (pf_by_row) {
-        // whole K / V streams of the first pf_pct % of the utterances (each projection a quarter of every stream):
-        // in the attention launch the CTAs of those rows run out of L2 and leave early while the other rows keep
-        // HBM streaming the whole time -- a prefix of EVERY stream instead makes all CTAs alternate between an
-        // L2 phase (HBM idle) and an HBM phase in lock step
-        pf.b_count = std::max(1, B * pf_pct / 100);
-        pf.lo_pct = 25 * quarter; pf.hi_pct = 25 * (quarter + 1);
-      } else {
-        pf.lo_pct = pf_pct * quarter / 4; pf.hi_pct = pf_pct * (quarter + 1) / 4;
-      }
+      pf.lo_pct = pf_pct * quarter / 4; pf.hi_pct = pf_pct * (quarter + 1) / 4;
       return pf;
     };
     for (int l = 0; l < D.n_layer; ++l) {

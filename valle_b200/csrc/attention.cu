@@ -427,7 +427,7 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
                    const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
                    const int32_t *__restrict__ n_gen, const int32_t *__restrict__ finished,
                    float *__restrict__ out, bf16 *__restrict__ out16,
-                   float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit, int pf_k_from, int pf_v_from) {
+                   float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit) {
   __shared__ float sc[kDecMaxChunk];
   __shared__ __align__(16) float qs[HD];
   __shared__ __align__(16) float knew[HD];
@@ -460,20 +460,6 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
 #pragma unroll
       for (int u = 0; u < U; ++u)
         kraw[u] = ldg_stream16(kb + (int64_t)(c0 + min(u * 16 + warp * 4 + g, n - 1)) * HD + j8);
-      // HBM -> L2 decoupled from L2 -> SM: the part of this CTA's K and V streams that the projection chain did not
-      // already pull into L2 is requested from the bulk-copy engine right away, so HBM keeps streaming while the
-      // warps consume the L2-resident head (all CTAs of the single wave run their phases in lock step; without
-      // this HBM idles whenever they read resident lines, sit in the softmax barrier or start the V pass)
-      if (tid == 0) {
-        if (pf_k_from >= 0) {
-          const int r = min(n, n * pf_k_from / 100 + 16 * U);
-          bulk_prefetch_l2(kb + (int64_t)(c0 + r) * HD, (uint32_t)((n - r) * HD * (int)sizeof(T)));
-        }
-        if (pf_v_from >= 0) {
-          const int r = n * pf_v_from / 100;
-          bulk_prefetch_l2(vb_ + (int64_t)(c0 + r) * HD, (uint32_t)((n - r) * HD * (int)sizeof(T)));
-        }
-      }
     }
   };
   // (only with the fused QKV prologue: there the current token's row is served from shared memory; without it the
@@ -692,13 +678,9 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
                             (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, finished, out,
                             (bf16 *)out16, part_o, part_ml, ns));
   } else {
-    // start of the region (percent of each stream) the kernel itself prefetches into L2 at launch; -1 = off.
-    // The projection chain prefetches [0, VB_KV_PREFETCH_PCT) of the next launch's streams (api.cu)
-    const int pf_k = tune("VB_ATTN_PF_K_FROM", -1);
-    const int pf_v = tune("VB_ATTN_PF_V_FROM", -1);
     VB_CUDA(launch_kernel(attn_decode_2phase_pf_kernel<8>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
                           (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, finished, out,
-                          (bf16 *)out16, part_o, part_ml, ns, B >= 16 ? pf_k : -1, B >= 16 ? pf_v : -1));
+                          (bf16 *)out16, part_o, part_ml, ns));
   }
   count_launch();
   if (ns > 1) {

@@ -122,12 +122,6 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// asynchronous L2 prefetch of a contiguous byte range by the bulk-copy engine (cp.async.bulk.prefetch.L2, SASS
-// UBLKPF.L2): one instruction, no registers or LSU slots held; p 16-byte aligned, bytes a multiple of 16
-__device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) {
-  if (bytes > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 // ---- grid-wide barrier of a cooperative launch (every CTA resident).  `ctr` is a monotonic arrival counter zeroed
 // before the launch; `target` (thread 0) advances by gridDim.x per barrier.  mode 0: every CTA polls the counter with
 // ld.acquire (simplest, but ~150 pollers hammer one L2 line and delay the late arrivals' atomics); mode 1: polling

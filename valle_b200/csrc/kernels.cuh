@@ -36,16 +36,13 @@ struct KvPrefetch {
   int B, H, cap, row_bytes;   // row_bytes = 64 * element size
   const int32_t *text_len, *prompt_len, *n_gen;
   int lo_pct, hi_pct;
-  int bulk;     // 1: one cp.async.bulk.prefetch.L2 per stream slice; 0: one prefetch.global.L2 per 128-byte line
-  int b_count;  // 0: the slice [lo_pct, hi_pct) of EVERY stream; > 0: only the streams of utterances [0, b_count)
 };
 // worker = one warp; `n_workers` warps of the grid share the streams.  Lane i of a warp fetches the lengths of the
 // warp's i-th stream up front (the three dependent global loads per stream would otherwise serialise the loop).
 __device__ __forceinline__ void kv_prefetch(const KvPrefetch &pf, int worker, int n_workers) {
   if (pf.kbase == nullptr) return;
   const int lane = threadIdx.x & 31;
-  const int nb = pf.b_count > 0 ? min(pf.b_count, pf.B) : pf.B;   // b_count > 0: whole streams of the first b_count rows
-  const int n_streams = 2 * nb * pf.H;
+  const int n_streams = 2 * pf.B * pf.H;
   int kv_mine = 0;
   {
     const int s_mine = worker + lane * n_workers;
@@ -67,10 +64,6 @@ __device__ __forceinline__ void kv_prefetch(const KvPrefetch &pf, int worker, in
     const int r_lo = kv * pf.lo_pct / 100, r_hi = kv * pf.hi_pct / 100;
     const char *p = (const char *)((sidx & 1) ? pf.vbase : pf.kbase) + (int64_t)b * pf.seq_stride_bytes +
                     ((int64_t)h * pf.cap + r_lo) * pf.row_bytes;
-    if (pf.bulk) {
-      if (lane == 0) bulk_prefetch_l2(p, (uint32_t)((r_hi - r_lo) * pf.row_bytes) & ~15u);
-      continue;
-    }
     const int lines = ((r_hi - r_lo) * pf.row_bytes) >> 7;  // 128-byte lines
     for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + ((int64_t)l << 7)));
   }
