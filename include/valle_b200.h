@@ -308,7 +308,9 @@ int vb_nar_argmax_accumulate(const float *logits, int64_t n_rows, int n_vocab, i
 int vb_cross_entropy(const float *logits, int64_t ld_logits, const int64_t *targets, int64_t n_rows,
                      int n_vocab, int64_t ignore_index, float *loss, vb_stream_t stream);
 
-/* gather rows: dst[r,:] = src[rows[r],:]  (fp32), used for "last position" / target slices */
+/* gather rows: dst[r,:] = src[rows[r],:], a zero row where rows[r] < 0  (fp32): "last position" / target slices, and
+ * the shifted copies (zero 'same' padding at the sequence ends) that turn the kernel-5 Conv1d of the text pre-net
+ * (valle/models/valle.py:97-113,182-204) into one vb_linear over [rows, 5 d] */
 int vb_gather_rows(const float *src, int64_t src_row_stride, const int32_t *rows, int64_t n_rows,
                    int d, float *dst, int64_t dst_row_stride, vb_stream_t stream);
 

@@ -207,16 +207,29 @@ def gen_topk(ref):
                               weight_seed=seed, checksums=checksums(m.state_dict()), x=x, y=y, cases=cases))
 
 
-def gen_switches(ref):
+def gen_switches(ref, only=()):
     """the constructor switches beyond the north-star configuration that the engine builds: prepend_bos (valle.py:
-    1006-1007,1059-1065,329-332) and nar_scale_factor != 1 (valle.py:83,231-247): greedy inference codes and the
+    1006-1007,1059-1065,329-332), nar_scale_factor != 1 (valle.py:83,231-247) and add_prenet (valle.py:96-131,
+    181-214, with randomised BatchNorm running statistics stored in the fixture): greedy inference codes and the
     training losses of a small padded batch, from the unmodified reference"""
     import random
-    for name, d, h, l, bos, f in (("tiny_bos", 256, 4, 2, True, 1.0), ("tiny_scale", 512, 8, 2, False, 0.5)):
+    for name, d, h, l, bos, f, pre in (("tiny_bos", 256, 4, 2, True, 1.0, False), ("tiny_scale", 512, 8, 2, False, 0.5, False),
+                                       ("tiny_prenet", 256, 4, 2, False, 1.0, True)):
+        if only and name not in only:
+            continue
         torch.manual_seed(0)
-        m = ref.VALLE(d, h, l, norm_first=True, add_prenet=False, prefix_mode=1, share_embedding=True,
+        m = ref.VALLE(d, h, l, norm_first=True, add_prenet=pre, prefix_mode=1, share_embedding=True,
                       nar_scale_factor=f, prepend_bos=bos, num_quantizers=8).eval()
         g = torch.Generator().manual_seed(31)
+        buffers = {}
+        if pre:   # non-trivial BatchNorm running statistics (a fresh module has mean 0 / var 1)
+            for k, v in m.named_buffers():
+                if k.endswith("running_mean"):
+                    v.copy_(torch.randn(v.shape, generator=g) * 0.05)
+                elif k.endswith("running_var"):
+                    v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+                if k.endswith(("running_mean", "running_var")):
+                    buffers[k] = v.clone()
         x, y = make_inputs(g, 6, 14)
         xl = torch.tensor([x.shape[1]], dtype=torch.int32)
         with torch.no_grad():
@@ -236,8 +249,8 @@ def gen_switches(ref):
         fw.update(x=xx, x_lens=xls, y=yy.to(torch.int16), y_lens=yls, torch_seed=5)
         print(f"{name}: frames={codes.shape[1]} losses={[float(fw[f'loss_stage{s}']) for s in (0, 1, 2)]}")
         save(f"{name}.pt", dict(config=dict(d_model=d, nhead=h, num_layers=l, prefix_mode=1, num_quantizers=8,
-                                            prepend_bos=bos, nar_scale_factor=f),
-                                weight_seed=0, checksums=checksums(m.state_dict()), x=x, y=y,
+                                            prepend_bos=bos, nar_scale_factor=f, add_prenet=pre),
+                                weight_seed=0, checksums=checksums(m.state_dict()), buffers=buffers, x=x, y=y,
                                 codes=codes.to(torch.int16), forward=fw))
 
 
@@ -255,6 +268,8 @@ def main(argv):
         gen_big(ref, 6, 30, "big_short")
     if "switches" in what:
         gen_switches(ref)
+    if "prenet" in what:
+        gen_switches(ref, only=("tiny_prenet",))
     if "topk" in what:
         gen_topk(ref)
     if "big_full" in what:

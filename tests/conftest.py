@@ -24,7 +24,7 @@ def build_model(cfg, seed, device="cpu"):
     import torch
     from valle_b200.models import VALLE
     torch.manual_seed(seed)
-    m = VALLE(cfg["d_model"], cfg["nhead"], cfg["num_layers"], norm_first=True, add_prenet=False,
+    m = VALLE(cfg["d_model"], cfg["nhead"], cfg["num_layers"], norm_first=True, add_prenet=cfg.get("add_prenet", False),
               prefix_mode=cfg["prefix_mode"], share_embedding=True, nar_scale_factor=cfg.get("nar_scale_factor", 1.0),
               prepend_bos=cfg.get("prepend_bos", False), num_quantizers=cfg["num_quantizers"]).eval()
     return m.to(device)

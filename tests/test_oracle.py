@@ -116,12 +116,14 @@ def test_oracle_vs_reference_inference_and_forward(pm):
 
 
 @needs_ref
-def test_model_mirror_matches_reference_checkpoint_layout():
-    """valle_b200.models.VALLE: same state_dict keys, shapes, init values and strict loading."""
+@pytest.mark.parametrize("prenet", [False, True])
+def test_model_mirror_matches_reference_checkpoint_layout(prenet):
+    """valle_b200.models.VALLE: same state_dict keys, shapes, init values and strict loading -- also with the
+    pre-nets of add_prenet=True (Conv1d / BatchNorm1d / Linear containers at the reference's Sequential indices)."""
     ref = load_reference()
-    cfg = dict(d_model=256, nhead=4, num_layers=2, prefix_mode=1, num_quantizers=8)
+    cfg = dict(d_model=256, nhead=4, num_layers=2, prefix_mode=1, num_quantizers=8, add_prenet=prenet)
     torch.manual_seed(0)
-    a = ref.VALLE(256, 4, 2, norm_first=True, add_prenet=False, prefix_mode=1, share_embedding=True,
+    a = ref.VALLE(256, 4, 2, norm_first=True, add_prenet=prenet, prefix_mode=1, share_embedding=True,
                   nar_scale_factor=1.0, prepend_bos=False, num_quantizers=8)
     b = build_model(cfg, 0)
     sa, sb = a.state_dict(), b.state_dict()
@@ -130,4 +132,5 @@ def test_model_mirror_matches_reference_checkpoint_layout():
     b.load_state_dict(sa, strict=True)
     a.load_state_dict(sb, strict=True)
     assert [n for n, _ in a.named_parameters()] == [n for n, _ in b.named_parameters()]
-    assert len(list(b.named_buffers())) == 0
+    assert [n for n, _ in a.named_buffers()] == [n for n, _ in b.named_buffers()]
+    assert (len(list(b.named_buffers())) == 0) == (not prenet)

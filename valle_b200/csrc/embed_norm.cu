@@ -177,10 +177,11 @@ __global__ void gather_rows_kernel(const float *__restrict__ src, int64_t src_ro
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= n_rows) return;
   const int lane = threadIdx.x & 31;
-  const float *s = src + (int64_t)rows[r] * src_row_stride;
+  const int32_t sr = rows[r];
+  const float *s = src + (int64_t)sr * src_row_stride;
   float *o = dst + r * dst_row_stride;
-  for (int c = lane * 4; c < d; c += 128)
-    *reinterpret_cast<float4 *>(o + c) = *reinterpret_cast<const float4 *>(s + c);
+  for (int c = lane * 4; c < d; c += 128)   // a negative index yields a zero row (the 'same' padding of the pre-net convs)
+    *reinterpret_cast<float4 *>(o + c) = sr >= 0 ? *reinterpret_cast<const float4 *>(s + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 }  // namespace vb

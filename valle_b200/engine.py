@@ -188,7 +188,7 @@ class ValleEngine:
 
     # ---- weights -----------------------------------------------------------------------
     def _signature(self):
-        return tuple((q.data_ptr(), q._version) for q in self.model.parameters())
+        return tuple((q.data_ptr(), q._version) for q in list(self.model.parameters()) + list(self.model.buffers()))
 
     def _refresh(self):
         sig = self._signature()
@@ -204,6 +204,63 @@ class ValleEngine:
         self.nar_predict_w = [cast(l.weight) for l in m.nar_predict_layers] if self.Q > 1 else []
         self._ada_cache = None
         self._bufs.clear()  # graphs hold stale weight pointers
+        self._prep_prenets()
+
+    # ---- pre-nets (add_prenet=True, valle.py:96-131,181-214; eval mode: Dropout = identity, BatchNorm1d on its
+    #      running statistics) ------------------------------------------------------------------
+    def _prep_prenets(self):
+        """fp32 weights of the four pre-nets in the layout the kernels take: every Conv1d(k=5, 'same') + BatchNorm1d
+        pair becomes ONE [Cout, 5 Cin] matrix (the batch-norm scale / shift folded into weight and bias, columns in
+        shift-major order to match `_im2col`), and the AR audio pre-net -- a function of the single embedded token
+        (valle.py:1013-1014) -- becomes a pre-computed table over the 1025 (+BOS) ids."""
+        m = self.model
+        self.pre = None
+        self.ar_audio_table = m.ar_audio_embedding.weight.detach()
+        if not getattr(m, "add_prenet", False):
+            return
+
+        def text(seq):
+            convs = []
+            for i in (1, 5, 9):
+                conv, bn = seq[i], seq[i + 1]
+                scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float()
+                w = conv.weight.detach().float() * scale[:, None, None]                   # [Cout, Cin, 5]
+                b = (conv.bias.detach().float() - bn.running_mean.float()) * scale + bn.bias.detach().float()
+                convs.append((w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous(), b.contiguous()))
+            return convs, (seq[14].weight.detach().float().contiguous(), seq[14].bias.detach().float().contiguous())
+
+        def audio(seq):
+            return [(seq[i].weight.detach().float().contiguous(), seq[i].bias.detach().float().contiguous())
+                    for i in (0, 3, 6)]
+
+        self.pre = {"ar_text": text(m.ar_text_prenet), "ar_audio": audio(m.ar_audio_prenet)}
+        if self.Q > 1:
+            self.pre["nar_text"] = text(m.nar_text_prenet)
+            self.pre["nar_audio"] = audio(m.nar_audio_prenet)
+        self.ar_audio_table = self._audio_prenet(m.ar_audio_embedding.weight.detach().float().contiguous(), "ar_audio")
+
+    def _audio_prenet(self, x: torch.Tensor, which: str) -> torch.Tensor:
+        (w1, b1), (w2, b2), (w3, b3) = self.pre[which]
+        h = ops.linear(x, w1, b1, L.VB_EPI_RELU)
+        h = ops.linear(h, w2, b2, L.VB_EPI_RELU)
+        return ops.linear(h, w3, b3, L.VB_EPI_NONE)
+
+    def _text_prenet(self, x: torch.Tensor, S: Sequence[int], which: str) -> torch.Tensor:
+        """x: packed [sum(S), d] embedded phonemes, utterance after utterance -> the pre-net output, same layout; every
+        utterance is convolved on its own with zero padding, as the reference's batch-1 call does (valle.py:995-996)"""
+        convs, (wl, bl) = self.pre[which]
+        R, d = x.shape
+        starts = np.cumsum([0] + list(S[:-1]), dtype=np.int64)
+        base, pos = _seg_ranges(starts, S)                   # row index, position inside its utterance
+        lens = np.repeat(np.asarray(S, dtype=np.int64), S)
+        idx = np.stack([np.where((pos + k - 2 >= 0) & (pos + k - 2 < lens), base + k - 2, -1) for k in range(5)])
+        idx_d = torch.from_numpy(idx.astype(np.int32)).to(self.device)
+        for (w, b) in convs:
+            xc = torch.empty((R, 5 * d), dtype=torch.float32, device=self.device)
+            for k in range(5):
+                ops.gather_rows(x, idx_d[k], out=xc[:, k * d:(k + 1) * d])
+            x = ops.linear(xc, w, b, L.VB_EPI_RELU)
+        return ops.linear(x, wl, bl, L.VB_EPI_NONE)
 
     def _pe(self, module, n: int) -> torch.Tensor:
         return module.table(n, self.device)
@@ -218,7 +275,7 @@ class ValleEngine:
         h = L.ArHead()
         h.predict_w = self.ar_predict_w.data_ptr()
         h.n_vocab, h.eos_id = self.n_vocab, NUM_AUDIO_TOKENS
-        h.audio_emb = m.ar_audio_embedding.weight.detach().data_ptr()
+        h.audio_emb = self.ar_audio_table.data_ptr()      # the embedding table, or pre-net(embedding) (add_prenet)
         h.alpha = m.ar_audio_position.alpha.detach().data_ptr()
         h.pe, h.pe_rows = pe.data_ptr(), pe.shape[0]
         h.greedy = int(greedy)
@@ -336,11 +393,12 @@ class ValleEngine:
         pe_t = self._pe(m.ar_text_position, max(S))
         pe_a = self._pe(m.ar_audio_position, max(Tp) + max(cap_new) + 2)
         x = torch.empty((M, d), dtype=torch.float32, device=dev)
-        self._embed_pe(text_all, 1, m.ar_text_embedding.weight, pe_t, m.ar_text_position.alpha, sum(S), x, trow_d, tpos_d)
+        self._embed_pe(text_all, 1, m.ar_text_embedding.weight, pe_t, m.ar_text_position.alpha, sum(S), x, trow_d, tpos_d,
+                       prenet=("ar_text", S) if self.pre else None)
         if self.prepend_bos:
-            self._embed_pe(ar_tok, 1, m.ar_audio_embedding.weight, pe_a, m.ar_audio_position.alpha, sum(Tp), x, arow_d, apos_d)
+            self._embed_pe(ar_tok, 1, self.ar_audio_table, pe_a, m.ar_audio_position.alpha, sum(Tp), x, arow_d, apos_d)
         else:
-            self._embed_pe(prm_all, Q, m.ar_audio_embedding.weight, pe_a, m.ar_audio_position.alpha, sum(Tp), x, arow_d, apos_d)
+            self._embed_pe(prm_all, Q, self.ar_audio_table, pe_a, m.ar_audio_position.alpha, sum(Tp), x, arow_d, apos_d)
         self.ar.forward(x, cu_d, B, max(seq_len), L.VB_MASK_VALLE_AR, S_d, None, buf.kcache, buf.vcache, cap)
         h_last = ops.gather_rows(x, last_d)
         head = self._head(pe_a, greedy)
@@ -460,11 +518,13 @@ class ValleEngine:
         return int(self.lib.vb_launch_count()) - self.captured_launches + self.replayed_launches
 
     # ---- helpers ---------------------------------------------------------------------------
-    def _embed_pe(self, tokens, tok_stride, table, pe, alpha, n, x, rows, pos):
-        """x[rows[r]] = table[tokens[r*tok_stride]] + alpha * pe[pos[r]]  (embedding then position,
-        valle.py:995-997 / 1013-1015)."""
+    def _embed_pe(self, tokens, tok_stride, table, pe, alpha, n, x, rows, pos, prenet=None):
+        """x[rows[r]] = prenet(table[tokens[r*tok_stride]]) + alpha * pe[pos[r]]  (embedding, pre-net, position:
+        valle.py:994-997 / 1013-1015); prenet = (name, lengths) of a text pre-net or None (identity)."""
         tmp = torch.empty((n, table.shape[1]), dtype=torch.float32, device=self.device)
         ops.embed_sum(tokens, tok_stride, 0, [table.detach()], n, tmp)
+        if prenet is not None:
+            tmp = self._text_prenet(tmp, prenet[1], prenet[0])
         ops.add_pe(tmp, pe, alpha.detach(), x, n, positions=pos, out_rows=rows)
 
     def _use_views(self, buf: _ArBuffers, greedy: bool) -> bool:
@@ -637,10 +697,20 @@ class ValleEngine:
         ada = self._ada_tables()
         x = torch.empty((M, d), dtype=torch.float32, device=dev)
         logits = torch.empty((G, NUM_AUDIO_TOKENS), dtype=torch.float32, device=dev)
+        x_text = None
+        if self.pre:   # valle.py:1081-1083: the text side (embedding, pre-net) is computed once for all stages
+            x_text = torch.empty((sum(S2), d), dtype=torch.float32, device=dev)
+            ops.embed_sum(text_nar, 1, 0, [m.nar_text_embedding.weight.detach()], sum(S2), x_text)
+            x_text = self._text_prenet(x_text, S2, "nar_text")
         for i in range(Q - 1):
             # xy_pos = concat([nar_text_position(nar_text_embedding(text)), nar_audio_position(y_emb)])
-            self._embed_pe(text_nar, 1, m.nar_text_embedding.weight, pe_t, m.nar_text_position.alpha, sum(S2), x, trow_d, tpos_d)
-            ops.add_pe(y_emb, pe_a, m.nar_audio_position.alpha.detach(), x, NT, positions=ypos_d, out_rows=yrow_d)
+            if x_text is not None:
+                ops.add_pe(x_text, pe_t, m.nar_text_position.alpha.detach(), x, sum(S2), positions=tpos_d, out_rows=trow_d)
+            else:
+                self._embed_pe(text_nar, 1, m.nar_text_embedding.weight, pe_t, m.nar_text_position.alpha, sum(S2), x, trow_d, tpos_d)
+            # valle.py:1092,1121: y_pos = nar_audio_position(nar_audio_prenet(y_emb))
+            y_in = self._audio_prenet(y_emb, "nar_audio") if self.pre else y_emb
+            ops.add_pe(y_in, pe_a, m.nar_audio_position.alpha.detach(), x, NT, positions=ypos_d, out_rows=yrow_d)
             self.nar.forward(x, cu_d, B, max(Ltot), L.VB_MASK_FULL, None, ada[i])
             hn = self.nar.final_norm(x, ada[i], rows=tgt_d, out_dtype=self.dtype)
             ops.linear(hn, self.nar_predict_w[i], None, L.VB_EPI_NONE, out=logits)

@@ -68,6 +68,30 @@ class PromptedFeatures:
         return (self.prompts, self.features)
 
 
+class Transpose(nn.Identity):
+    """(N, T, D) -> (N, D, T) (valle/utils/__init__.py); parameter-free, position 0 / 13 of the text pre-net"""
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        return input.transpose(1, 2)
+
+
+def _text_prenet(d: int) -> nn.Sequential:
+    """valle.py:97-113 / 182-204: 3 x (Conv1d k=5 'same' -> BatchNorm1d -> ReLU -> Dropout(0.5)) between two
+    transposes, then Linear.  Parameter container with the reference's state_dict keys (ar_text_prenet.1.weight ...);
+    the arithmetic runs in the engine (ValleEngine._text_prenet)."""
+    layers: List[nn.Module] = [Transpose()]
+    for _ in range(3):
+        layers += [nn.Conv1d(d, d, kernel_size=5, padding="same"), nn.BatchNorm1d(d), nn.ReLU(), nn.Dropout(0.5)]
+    layers += [Transpose(), nn.Linear(d, d)]
+    return nn.Sequential(*layers)
+
+
+def _audio_prenet(d: int) -> nn.Sequential:
+    """valle.py:115-123 / 205-213: Linear(d,256) ReLU Dropout(0.25) Linear(256,256) ReLU Dropout(0.25) Linear(256,d)"""
+    return nn.Sequential(nn.Linear(d, 256), nn.ReLU(), nn.Dropout(0.25), nn.Linear(256, 256), nn.ReLU(),
+                         nn.Dropout(0.25), nn.Linear(256, d))
+
+
 class VALLE(nn.Module):
     """Decoder-only VALL-E (https://arxiv.org/abs/2301.02111): AR stack + NAR stack."""
 
@@ -77,10 +101,11 @@ class VALLE(nn.Module):
         super().__init__()
         prepend_bos = bool(kwargs.pop("prepend_bos", False))
         num_quantizers = int(kwargs.pop("num_quantizers", 8))
-        if add_prenet or not norm_first:
+        if not norm_first:
             raise NotImplementedError(
-                "valle_b200.VALLE: add_prenet=True (conv / linear pre-nets, valle.py:96-131,181-214) and post-LN "
-                "(norm_first=False) are not built; prepend_bos and nar_scale_factor are (DESIGN.md section 7)")
+                "valle_b200.VALLE: post-LN (norm_first=False) is not built; add_prenet, prepend_bos and "
+                "nar_scale_factor are (DESIGN.md section 7)")
+        self.add_prenet = bool(add_prenet)
         nar_d_model = int(d_model * nar_scale_factor)
         if nar_d_model % 256 != 0 or nar_d_model // max(1, int(nhead * nar_scale_factor)) != 64:
             raise NotImplementedError("valle_b200.VALLE: nar_scale_factor must keep d_model a multiple of 256 and 64-wide heads")
@@ -89,8 +114,8 @@ class VALLE(nn.Module):
         self.nar_text_embedding = TokenEmbedding(nar_d_model, NUM_TEXT_TOKENS)
         self.ar_audio_prepend_bos = prepend_bos
         self.ar_audio_embedding = TokenEmbedding(d_model, NUM_AUDIO_TOKENS + 1 + int(prepend_bos))
-        self.ar_text_prenet = nn.Identity()
-        self.ar_audio_prenet = nn.Identity()
+        self.ar_text_prenet = _text_prenet(d_model) if add_prenet else nn.Identity()
+        self.ar_audio_prenet = _audio_prenet(d_model) if add_prenet else nn.Identity()
         self.ar_text_position = SinePositionalEmbedding(d_model, dropout=0.1, scale=False, alpha=True)
         self.ar_audio_position = SinePositionalEmbedding(d_model, dropout=0.1, scale=False, alpha=True)
         self.ar_decoder = TransformerEncoder(
@@ -107,8 +132,8 @@ class VALLE(nn.Module):
             self.nar_audio_embeddings = nn.ModuleList(
                 [TokenEmbedding(nar_d_model, NUM_AUDIO_TOKENS + 1)]
                 + [TokenEmbedding(nar_d_model, NUM_AUDIO_TOKENS) for _ in range(num_quantizers - 1)])
-            self.nar_text_prenet = nn.Identity()
-            self.nar_audio_prenet = nn.Identity()
+            self.nar_text_prenet = _text_prenet(nar_d_model) if add_prenet else nn.Identity()
+            self.nar_audio_prenet = _audio_prenet(nar_d_model) if add_prenet else nn.Identity()
             self.nar_text_position = SinePositionalEmbedding(nar_d_model, dropout=0.0, scale=False, alpha=False)
             self.nar_audio_position = SinePositionalEmbedding(nar_d_model, dropout=0.1, scale=False, alpha=False)
             self.nar_decoder = TransformerEncoder(

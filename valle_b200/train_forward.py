@@ -88,11 +88,23 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
     metrics: Dict[str, torch.Tensor] = {}
     total_loss = torch.zeros((), device=dev)
     x_emb_out = None
+    eng = None
+    if getattr(model, "add_prenet", False):
+        # valle.py:830,864,898,918: pre-nets between embedding and position.  Evaluation only: BatchNorm1d on its running
+        # statistics (folded into the conv weights by the engine), Dropout = identity
+        if want_grad or model.training:
+            raise NotImplementedError("valle_b200: training with add_prenet=True (BatchNorm batch statistics, pre-net "
+                                      "dropout and their gradients) is not built; evaluation and inference are")
+        eng = model.engine()
+        eng._refresh()
 
-    def embed_pe(tokens, table, pos_mod, T):
-        """[N, T] ids -> [N, T, d] = table[ids] + alpha * pe[:T]."""
+    def embed_pe(tokens, table, pos_mod, T, text_prenet=None):
+        """[N, T] ids -> [N, T, d] = prenet(table[ids]) + alpha * pe[:T]."""
         tok = tokens.reshape(-1).contiguous()
         e = AG.EmbedSum.apply(tok, 1, 0, tok.numel(), table)
+        if eng is not None and text_prenet is not None:
+            # the reference convolves the padded batch: pad-token embeddings inside, zeros beyond the longest text
+            e = eng._text_prenet(e, [T] * N, text_prenet)
         return add_pe(e.view(N, T, table.shape[1]), pos_mod, T)
 
     def add_pe(e, pos_mod, T):
@@ -123,9 +135,10 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
 
     # ---- AR decoder (valle.py:828-881) ----
     if train_stage in (0, 1):
-        xe = embed_pe(text, model.ar_text_embedding.weight, model.ar_text_position, Smax)
+        xe = embed_pe(text, model.ar_text_embedding.weight, model.ar_text_position, Smax, "ar_text")
         Ta = yin.shape[1]                     # Tmax, or Tmax + 1 with the prepended <BOS> (valle.py:820-826,833)
-        ye = embed_pe(yin.contiguous(), model.ar_audio_embedding.weight, model.ar_audio_position, Ta)
+        ar_table = eng.ar_audio_table if eng is not None else model.ar_audio_embedding.weight   # pre-net(embedding)
+        ye = embed_pe(yin.contiguous(), ar_table, model.ar_audio_position, Ta)
         rows = torch.cat([xe, ye], dim=1).reshape(N * (Smax + Ta), d).contiguous()
         nd = model.ar_decoder.native(dtype)
         yl_ar = (yl32 + (Ta - Tmax)).contiguous()
@@ -146,7 +159,7 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
     if train_stage in (0, 2):
         num_nar_layers = Q - 1
         nar_stage = model.rng.choices([_k for _k in range(1, Q)], weights=[1.0 / num_nar_layers] * num_nar_layers, k=1)[0]
-        xe = embed_pe(text, model.nar_text_embedding.weight, model.nar_text_position, Smax)
+        xe = embed_pe(text, model.nar_text_embedding.weight, model.nar_text_position, Smax, "nar_text")
         emb = [e.weight for e in model.nar_audio_embeddings]
         yq = codes[..., 0].contiguous()
         pm = model.prefix_mode
@@ -189,6 +202,8 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
             seg1 = (yl32 + (Ty - Tmax)).contiguous()   # key mask F.pad(y_mask, (prefix, 0), False) valle.py:908-914
         elif pm == 1:
             tg = tg[:, prefix_len:]
+        if eng is not None:   # valle.py:918
+            y_emb = eng._audio_prenet(y_emb.reshape(N * Ty, -1).contiguous(), "nar_audio").view(N, Ty, -1)
         y_pos = add_pe(y_emb.contiguous(), model.nar_audio_position, Ty)
         Lp = Smax + Ty
         rows = torch.cat([xe, y_pos], dim=1).reshape(N * Lp, xe.shape[-1]).contiguous()
