@@ -29,7 +29,7 @@ constexpr int kKBytes = BKV * HD * 2;        // 16 KB
 constexpr int kStageBytes = 2 * kKBytes;     // K + V
 constexpr int kStages = 2;
 constexpr int kPBytes = BQ * BKV * 2;        // 32 KB (two 64-key K-blocks of [128 x 64])
-constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kPBytes + 96 + 512;  // + barriers, TMEM slot
+constexpr int kSmemBytes = kQBytes + kStages * kStageBytes + kPBytes + 128 + 480;  // + barriers, TMEM slot
 static_assert(2 * (kSmemBytes + 1024) <= 228 * 1024, "two CTAs per SM must fit");
 constexpr int kTmemCols = 256;               // S_0, S_1, O_0, O_1: 64 columns each
 
@@ -395,6 +395,296 @@ attn_tcgen05_pp_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, con
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Persistent form of the same pipeline: 2 CTAs per SM, each walking the work items
+// (query tile, head, sequence) w = blockIdx.x, blockIdx.x + gridDim.x, ...  A CTA of the one-item-per-CTA kernel
+// above spends ~2.7 us in front of its first softmax round (barrier / TMEM setup, Q and K/V loads from a cold start,
+// first MMA) and ~2 us behind the last one (accumulator drain, merge, stores) out of a ~19 us life at L = 1024
+// (profiles/round2_fa_rr_experiment_regions.csv).  Here the TMA warp runs ahead across item boundaries (the K/V
+// ring never drains; Q of the next item is fetched as soon as the last S MMA of the current one has retired), the MMA
+// warp issues the next item's first scores while the softmax warps are still merging the current one, and the
+// barriers keep running phase counters instead of being re-initialised.
+struct Item {
+  int b, h, q0, r0, L, S, c1, n_tiles;
+  bool valid;
+};
+__device__ __forceinline__ Item make_item(int w, int nq, int n_head, int n_items, const int32_t *cu_seqlens,
+                                          const int32_t *text_lens, const int32_t *seg1_lens, int mask_mode,
+                                          int skip_partial) {
+  Item it;
+  it.valid = false;
+  if (w >= n_items) return it;
+  const int qt = w % nq;
+  const int bh = w / nq;
+  it.h = bh % n_head;
+  it.b = bh / n_head;
+  it.r0 = cu_seqlens[it.b];
+  it.L = cu_seqlens[it.b + 1] - it.r0;
+  it.q0 = qt * BQ;
+  if (it.q0 >= it.L) return it;
+  if (it.q0 + BQ > it.L) {
+    if (skip_partial == 1) return it;
+    if (skip_partial == 2 && it.L >= BQ) it.q0 = it.L - BQ;
+  }
+  it.S = (mask_mode != VB_MASK_FULL) ? text_lens[it.b] : 0;
+  it.c1 = (mask_mode >= VB_MASK_PADDED_AR) ? seg1_lens[it.b] : 0;
+  const int q_hi = min(it.q0 + BQ, it.L);
+  const int kv_max = (mask_mode == VB_MASK_VALLE_AR) ? max(it.S, q_hi) : it.L;
+  it.n_tiles = (kv_max + BKV - 1) / BKV;
+  it.valid = it.n_tiles > 0;
+  return it;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+attn_tcgen05_persistent_kernel(const __grid_constant__ CUtensorMap tmap, int n_head, int nq, int n_items,
+                               const int32_t *__restrict__ cu_seqlens, const int32_t *__restrict__ text_lens,
+                               const int32_t *__restrict__ seg1_lens, int seg1_start, int mask_mode,
+                               bf16 *__restrict__ out, int skip_partial) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t *sQ = smem;
+  uint8_t *sKV = sQ + kQBytes;                       // [stage][K | V]
+  uint8_t *sP = sKV + kStages * kStageBytes;         // [group][128 rows x 128 B]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + kPBytes);
+  uint64_t *q_full = bars;              // Q tile of the current item landed
+  uint64_t *kv_full = bars + 1;         // [kStages]
+  uint64_t *kv_empty = kv_full + kStages;
+  uint64_t *s_full = kv_empty + kStages;   // [2] S_g ready in TMEM
+  uint64_t *p_full = s_full + 2;           // [2] P_g in smem, S_g consumed (4 warp arrivals)
+  uint64_t *o_done = p_full + 2;           // [2] P_g V accumulated: P_g buffer free, O_g stable
+  uint64_t *q_empty = o_done + 2;          // every S MMA of the item retired: the Q tile may be overwritten
+  uint64_t *o_free = q_empty + 1;          // the merge has read O_0 and O_1 (8 warp arrivals)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_free + 1);
+  static_assert((1 + 2 * kStages + 8) * 8 + 8 <= 128, "barrier block");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = n_head * HD;
+
+  if (warp == 0 && lane == 0) prefetch_tmap(&tmap);
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, 8);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&s_full[g], 1);
+      mbar_init(&p_full[g], 4);
+      mbar_init(&o_done[g], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: runs ahead of the consumers across item boundaries =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, n_done = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const Item it = make_item(w, nq, n_head, n_items, cu_seqlens, text_lens, seg1_lens, mask_mode, skip_partial);
+        if (!it.valid) continue;
+        mbar_wait(q_empty, (n_done & 1) ^ 1);            // passes at once for the first item
+        mbar_expect_tx(q_full, kQBytes);
+        tma_load_2d(&tmap, q_full, sQ, it.h * HD, it.r0 + it.q0);
+        for (int t = 0; t < it.n_tiles; ++t) {
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          uint8_t *dst = sKV + stage * kStageBytes;
+          mbar_expect_tx(&kv_full[stage], kStageBytes);
+          tma_load_2d(&tmap, &kv_full[stage], dst, d + it.h * HD, it.r0 + t * BKV);
+          tma_load_2d(&tmap, &kv_full[stage], dst + kKBytes, 2 * d + it.h * HD, it.r0 + t * BKV);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ++n_done;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(BQ, 64);       // S_g = Q K_g^T : both K-major, N = 64 keys
+      constexpr uint32_t idesc_o = make_idesc_bmn(BQ, HD);   // O_g += P_g V_g : A K-major, B MN-major
+      constexpr int kHalfBytes = 64 * HD * 2;                // 64 keys of a K or V tile = 8 swizzle atoms
+      const uint64_t qdesc = make_smem_desc(smem_u32(sQ));
+      int stage = 0;
+      uint32_t phase = 0, n_done = 0, round = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const Item it = make_item(w, nq, n_head, n_items, cu_seqlens, text_lens, seg1_lens, mask_mode, skip_partial);
+        if (!it.valid) continue;
+        const int n_tiles = it.n_tiles;
+        mbar_wait(q_full, n_done & 1);
+        mbar_wait(&kv_full[stage], phase);
+        tcgen05_fence_after();
+        for (int g = 0; g < 2; ++g) {        // S_g(0): the score buffers were consumed in the previous item's last round
+          const uint64_t kdesc = make_smem_desc(smem_u32(sKV + stage * kStageBytes + g * kHalfBytes));
+#pragma unroll
+          for (int k = 0; k < HD / UMMA_K; ++k)
+            umma_bf16(tmem_base + g * 64, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
+          tcgen05_commit(&s_full[g]);
+        }
+        if (n_tiles == 1) tcgen05_commit(q_empty);
+        for (int t = 0; t < n_tiles; ++t) {
+          const int vstage = stage;
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          for (int g = 0; g < 2; ++g) {
+            mbar_wait(&p_full[g], round & 1);          // P_g(t) written, S_g(t) consumed
+            tcgen05_fence_after();
+            if (t + 1 < n_tiles) {                    // S_g(t+1) first: its softmax group waits on it
+              if (g == 0) {
+                mbar_wait(&kv_full[stage], phase);
+                tcgen05_fence_after();
+              }
+              const uint64_t kdesc = make_smem_desc(smem_u32(sKV + stage * kStageBytes + g * kHalfBytes));
+#pragma unroll
+              for (int k = 0; k < HD / UMMA_K; ++k)
+                umma_bf16(tmem_base + g * 64, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
+              tcgen05_commit(&s_full[g]);
+              if (g == 1 && t + 2 == n_tiles) tcgen05_commit(q_empty);   // last S MMA of the item issued
+            }
+            if (t == 0 && g == 0 && n_done > 0) {      // the previous item's merge has read both accumulators
+              mbar_wait(o_free, (n_done - 1) & 1);
+              tcgen05_fence_after();
+            }
+            const uint64_t pdesc = make_smem_desc(smem_u32(sP + g * kQBytes));
+            const uint64_t vdesc = make_smem_desc_mn(smem_u32(sKV + vstage * kStageBytes + kKBytes + g * kHalfBytes));
+#pragma unroll
+            for (int k = 0; k < 64 / UMMA_K; ++k)
+              umma_bf16(tmem_base + 128 + g * 64, pdesc + (uint64_t)(k * 2), vdesc + (uint64_t)(k * (2048 >> 4)),
+                        idesc_o, (t > 0 || k > 0) ? 1u : 0u);
+            tcgen05_commit(&o_done[g]);
+          }
+          tcgen05_commit(&kv_empty[vstage]);  // K(t), V(t) free once these MMAs retire
+          ++round;
+        }
+        ++n_done;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax group g: one thread per query row, keys 128 t + 64 g .. + 63 =====
+    const int quarter = warp & 3;                  // TMEM lanes this warp may touch
+    const int g = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_off + g * 64;
+    const uint32_t o_addr = tmem_base + lane_off + 128 + g * 64;
+    uint8_t *p_row = sP + g * kQBytes + row * 128;
+    const float sc = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+    uint32_t round = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const Item it = make_item(w, nq, n_head, n_items, cu_seqlens, text_lens, seg1_lens, mask_mode, skip_partial);
+      if (!it.valid) continue;
+      const int n_tiles = it.n_tiles, L = it.L;
+      const int qr = it.q0 + row;
+      const RowMask rm = make_row_mask(mask_mode, qr, L, it.S, seg1_start, it.c1);
+      float m_ref = -CUDART_INF_F, l = 0.f;
+      for (int t = 0; t < n_tiles; ++t, ++round) {
+        const int jc0 = t * BKV + g * 64;
+        if (lane == 0) mbar_wait(&s_full[g], round & 1);
+        __syncwarp();
+        tcgen05_fence_after();
+        const bool interior = __all_sync(0xffffffffu, jc0 + 64 <= rm.lim0);
+        const float mx = interior ? half_row_max<false>(s_addr, rm, jc0) : half_row_max<true>(s_addr, rm, jc0);
+        const float m_cand = fmaxf(m_ref, mx * sc);
+        const bool need = (m_cand - m_ref) > 8.f;     // NaN (-inf - -inf) compares false
+        if (t > 0) {                                  // P_g buffer free, O_g stable
+          if (lane == 0) mbar_wait(&o_done[g], (round - 1) & 1);
+          __syncwarp();
+          tcgen05_fence_after();
+        }
+        if (__any_sync(0xffffffffu, need)) {
+          const float corr = (m_cand == m_ref) ? 1.f : ex2(m_ref - m_cand);
+          if (t > 0) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+              uint32_t r[32];
+              tmem_ld32(o_addr + c0, r);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * corr);
+              tmem_st32(o_addr + c0, r);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
+          l *= corr;
+          m_ref = m_cand;
+        }
+        const float m_use = m_ref == -CUDART_INF_F ? 0.f : m_ref;
+        l += interior ? half_row_p<false>(s_addr, rm, jc0, sc, m_use, p_row, row)
+                      : half_row_p<true>(s_addr, rm, jc0, sc, m_use, p_row, row);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P visible to the tensor-core proxy
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[g]);
+      }
+      // ---- merge the two key halves: out = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1), w_g = 2^(m_g - max) ----
+      if (lane == 0) {
+        mbar_wait(&o_done[0], (round - 1) & 1);
+        mbar_wait(&o_done[1], (round - 1) & 1);   // in-order retirement: every MMA of this item is done, so both P
+      }                                           // buffers are free and carry the (m, l) exchange
+      __syncwarp();
+      tcgen05_fence_after();
+      // exchange slots of query row r: the first 16 bytes of P_0's row r, which only thread (group 0, row r) writes
+      // again (next item, after the second pair barrier below)
+      float2 *xch = reinterpret_cast<float2 *>(sP + row * 128);
+      xch[g] = make_float2(m_ref, l);
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      const float2 e0 = xch[0], e1 = xch[1];
+      uint32_t a[32], c[32];
+      tmem_ld32(tmem_base + lane_off + 128 + g * 32, a);        // O_0, dims 32 g ..
+      tmem_ld32(tmem_base + lane_off + 192 + g * 32, c);        // O_1, same dims
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");   // both partners have read the exchange slots
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);            // the next item's first P V may overwrite the accumulators
+      const float mm = fmaxf(e0.x, e1.x);
+      const float w0 = e0.x == -CUDART_INF_F ? 0.f : ex2(e0.x - mm);
+      const float w1 = e1.x == -CUDART_INF_F ? 0.f : ex2(e1.x - mm);
+      const float inv = 1.f / (e0.y * w0 + e1.y * w1);
+      const float f0 = w0 * inv, f1 = w1 * inv;
+      if (qr < L) {
+        uint4 *dst = reinterpret_cast<uint4 *>(out + (int64_t)(it.r0 + qr) * d + it.h * HD + g * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t wv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = 8 * j + 2 * k;
+            const float x0 = __uint_as_float(a[i]) * f0 + __uint_as_float(c[i]) * f1;
+            const float x1 = __uint_as_float(a[i + 1]) * f0 + __uint_as_float(c[i + 1]) * f1;
+            __nv_bfloat162 v = __floats2bfloat162_rn(x0, x1);
+            wv[k] = *reinterpret_cast<uint32_t *>(&v);
+          }
+          dst[j] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
 }  // namespace fa5
 
 bool attention_tcgen05_enabled() { return getenv("VB_ATTN_MMA_SYNC") == nullptr; }
@@ -407,11 +697,21 @@ int launch_attention_tcgen05(const bf16 *qkv, int64_t M, int B, int n_head, cons
   CUtensorMap tm;
   VB_TRY(tc::make_tmap(&tm, qkv, M, 3 * d, 3 * (int64_t)d, fa5::BQ));
   static PerDeviceOnce once;
-  if (once.first())
+  if (once.first()) {
     VB_CUDA(cudaFuncSetAttribute(fa5::attn_tcgen05_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa5::kSmemBytes));
-  dim3 grid((max_seqlen + fa5::BQ - 1) / fa5::BQ, n_head, B);
-  fa5::attn_tcgen05_pp_kernel<<<grid, fa5::kThreads, fa5::kSmemBytes, s>>>(tm, n_head, cu_seqlens, text_lens, seg1_lens,
-                                                                         seg1_start, mask_mode, out, skip_partial);
+    VB_CUDA(cudaFuncSetAttribute(fa5::attn_tcgen05_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fa5::kSmemBytes));
+  }
+  const int nq = (max_seqlen + fa5::BQ - 1) / fa5::BQ;
+  const int64_t n_items = (int64_t)nq * n_head * B;
+  if (tune("VB_FA_PERSISTENT", 1) != 0 && n_items > 2 * sm_count() && n_items < (1ll << 31)) {
+    // more than one wave: 2 CTAs per SM walk the items
+    fa5::attn_tcgen05_persistent_kernel<<<2 * sm_count(), fa5::kThreads, fa5::kSmemBytes, s>>>(
+        tm, n_head, nq, (int)n_items, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, out, skip_partial);
+  } else {
+    dim3 grid(nq, n_head, B);
+    fa5::attn_tcgen05_pp_kernel<<<grid, fa5::kThreads, fa5::kSmemBytes, s>>>(tm, n_head, cu_seqlens, text_lens, seg1_lens,
+                                                                           seg1_start, mask_mode, out, skip_partial);
+  }
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
