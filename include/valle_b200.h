@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 2
+#define VB_ABI_VERSION 3
 
 enum vb_status { VB_OK = 0, VB_ERR_ARG = 1, VB_ERR_CUDA = 2, VB_ERR_UNSUPPORTED = 3 };
 /* storage type of the big matrices / activations.  Accumulation is always fp32. */
@@ -174,12 +174,25 @@ int vb_decoder_forward(vb_decoder_t dec, float *x, int64_t M, int B, const int32
  *     modules; parameter gradients are fp32 and ACCUMULATED (+=) into caller-zeroed buffers.
  * ---------------------------------------------------------------------------------------- */
 /* bytes of the activation store vb_decoder_forward_train fills for M rows (per layer: layer input, LN1 out, q|k|v,
- * attention out, post-attention residual, LN2 out, FFN hidden) */
+ * attention out, post-attention residual, LN2 out, FFN hidden; plus one [M, d] scratch row block) */
 size_t vb_decoder_train_save_bytes(const vb_decoder_desc *desc, int64_t M);
-/* vb_decoder_forward (no KV cache) that keeps the activations the backward pass needs in `save` */
+/* vb_decoder_forward (no KV cache) that keeps the activations the backward pass needs in `save`.
+ * dropout_p > 0 = training mode of valle/modules/transformer.py:315-334 and of the attention inside
+ * F.multi_head_attention_forward (activation.py:408-427, `dropout_p=self.dropout` when training): Bernoulli masks with
+ * keep probability 1 - p, survivors scaled by 1 / (1 - p), on the attention probabilities, on both sub-layer outputs
+ * ahead of the residual add and on the FFN hidden.  The masks are a stateless hash of (dropout_seed, layer, site,
+ * element index): vb_decoder_backward called with the same (p, seed) regenerates them, nothing is stored.  The
+ * reference draws its masks from torch's generator inside the kernels this library replaces, so individual masks
+ * differ from the reference's while their distribution does not. */
 int vb_decoder_forward_train(vb_decoder_t dec, float *x, int64_t M, int B, const int32_t *cu_seqlens,
                              const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
-                             int mask_mode, const float *ada_wb, void *save, size_t save_bytes, vb_stream_t stream);
+                             int mask_mode, const float *ada_wb, void *save, size_t save_bytes, float dropout_p,
+                             uint64_t dropout_seed, vb_stream_t stream);
+/* nn.Dropout on a contiguous tensor (embedding.py:97 after the positional encoding): out[i] = in[i] / (1 - p) where
+ * the hash of (seed, stream_id, i) keeps element i, else 0; in == out allowed.  Its own backward: the same call on
+ * the gradient. */
+int vb_dropout(const void *in, void *out, int dtype, int64_t n, float p, uint64_t seed, uint32_t stream_id,
+               vb_stream_t stream);
 
 typedef struct vb_layer_grads { /* fp32 gradient buffers of one layer, same shapes as vb_layer_params; NULL = skip */
   float *in_proj_w, *in_proj_b, *out_proj_w, *out_proj_b, *lin1_w, *lin1_b, *lin2_w, *lin2_b;
@@ -196,11 +209,12 @@ size_t vb_decoder_backward_workspace(const vb_decoder_desc *desc, int64_t M);
 /* Backward of vb_decoder_forward_train.  dx: fp32 [M, d], gradient w.r.t. the stack output on entry, w.r.t. the
  * stack input on return.  ada_wb / dada_wb: the AdaLN (weight|bias) rows of the forward call and their gradient
  * ([(2*n_layer+1), 2d], rows 2l / 2l+1 touched here), both NULL for a LayerNorm stack.  wt / grads: host arrays
- * [n_layer]. */
+ * [n_layer].  dropout_p / dropout_seed: the values of the forward call. */
 int vb_decoder_backward(vb_decoder_t dec, float *dx, int64_t M, int B, const int32_t *cu_seqlens,
                         const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
                         int mask_mode, const float *ada_wb, float *dada_wb, const void *save, const vb_layer_wt *wt,
-                        const vb_layer_grads *grads, void *workspace, size_t workspace_bytes, vb_stream_t stream);
+                        const vb_layer_grads *grads, void *workspace, size_t workspace_bytes, float dropout_p,
+                        uint64_t dropout_seed, vb_stream_t stream);
 
 /* LayerNorm / AdaptiveLayerNorm backward (transformer.py:57-108) of y = vb_layernorm(x rows): dx[xrow(r), :] +=
  * d/dx, optional copy of the updated dx rows in copy_dtype ([*, d] dense), dgamma / dbeta / dada_wb (2d: weight |

@@ -23,6 +23,28 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _no_dropout(m):
+    """train() mode with every Dropout site at p = 0 (comparisons against the dropout-free oracle)"""
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return m
+
+
+def _keep_mask(seed, stream, n, p, idx=None):
+    """the stateless mask of csrc/kernels.cuh::drop_keep restated in numpy: True = kept"""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        i = np.arange(n, dtype=np.uint64) if idx is None else idx.astype(np.uint64)
+        z = np.uint64(seed) + np.uint64(stream) * np.uint64(0x9E3779B97F4A7C15) + i * np.uint64(0xD1342543DE82EF95)
+        z ^= z >> np.uint64(30)
+        z *= np.uint64(0xBF58476D1CE4E5B9)
+        z ^= z >> np.uint64(27)
+        z *= np.uint64(0x94D049BB133111EB)
+        z ^= z >> np.uint64(31)
+        return torch.from_numpy(((z >> np.uint64(32)) >= np.uint64(int(p * 4294967296.0))).astype(np.bool_))
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
 def test_linear_backward_vs_autograd(dtype, tol):
     from valle_b200 import _lib as L
@@ -192,7 +214,7 @@ def test_valle_forward_backward_matches_reference_autograd(stage, dtype, tol):
     ref_loss, ref = _oracle_grads(g, stage, int(fw["nar_stage"]), int(fw["prefix_len"]))
     m = build_model(g["config"], g["weight_seed"])
     assert_checksums(m, g["checksums"])
-    m = m.to(DEV).train()
+    m = _no_dropout(m.to(DEV).train())     # the oracle differentiates the evaluation-mode forward
     m.engine_dtype = dtype
     m.rng = random.Random(0)
     torch.manual_seed(int(fw["torch_seed"]))
@@ -232,7 +254,7 @@ def test_optimizer_step_changes_the_next_forward():
     """one SGD step on the gradients lowers the loss of the same batch (the engine re-packs changed parameters)"""
     g = load_golden("config0.pt")
     fw = g["forward"]
-    m = build_model(g["config"], g["weight_seed"]).to(DEV).train()
+    m = _no_dropout(build_model(g["config"], g["weight_seed"]).to(DEV).train())
     opt = torch.optim.SGD(m.parameters(), lr=2e-6)   # sum-reduced loss over ~800 target positions: large gradients
     losses = []
     for _ in range(3):
@@ -244,3 +266,133 @@ def test_optimizer_step_changes_the_next_forward():
         opt.step()
         losses.append(float(loss))
     assert losses[2] < losses[1] < losses[0], losses
+
+
+# ---------------------------------------------------------------- training-mode dropout
+def test_dropout_mask_is_the_documented_hash_and_its_own_backward():
+    """vb_dropout: survivors scaled by 1 / (1 - p), mask = the splitmix hash of (seed, stream, index) restated in
+    numpy above, keep rate within 0.5 % of 1 - p, another stream gives another mask, backward = same mask on dy"""
+    from valle_b200 import autograd as AG
+    torch.manual_seed(0)
+    n, p, seed = 1 << 20, 0.1, 0x1234567890ABCDEF % (1 << 62)
+    x = (torch.randn(n, device=DEV) + 3.0).requires_grad_()
+    y = AG.Dropout.apply(x, p, seed, 7)
+    keep = _keep_mask(seed, 7, n, p).to(DEV)
+    assert torch.equal(y != 0, keep)
+    assert torch.allclose(y[keep], x.detach()[keep] / (1 - p), rtol=1e-6)
+    assert abs(float(keep.float().mean()) - (1 - p)) < 5e-3
+    assert not torch.equal(AG.Dropout.apply(x.detach(), p, seed, 8) != 0, keep)
+    y.sum().backward()
+    assert torch.allclose(x.grad, keep.float() / (1 - p), rtol=1e-6)
+    xb = x.detach().bfloat16()
+    yb = AG.Dropout.apply(xb, p, seed, 7)
+    assert torch.equal(yb != 0, keep)
+
+
+def _torch_stack_with_masks(x, layers, key_ok, p, seed, H):
+    """pre-LN TransformerEncoderLayer stack (transformer.py:296-334) in plain torch with the dropout masks of the
+    library's hash: x [N, L, d]; key_ok [N, L] bool (keys a row may attend to: the VB_MASK_PADDED rule)."""
+    N, Lq, d = x.shape
+    keep_scale = 1.0 / (1.0 - p)
+    for l, P in enumerate(layers):
+        h = F.layer_norm(x, (d,), P["n1w"], P["n1b"], 1e-5)
+        qkv = F.linear(h, P["wi"], P["bi"]).view(N, Lq, 3, H, 64)
+        q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))              # [N, H, L, 64]
+        sc = (q @ k.transpose(-1, -2)) * 0.125
+        sc = sc.masked_fill(~key_ok[:, None, None, :], float("-inf"))
+        pr = torch.softmax(sc, dim=-1)
+        m0 = _keep_mask(seed, (l << 2) | 0, N * H * Lq * Lq, p).view(N, H, Lq, Lq).to(x.device)
+        o = ((pr * m0 * keep_scale) @ v).transpose(1, 2).reshape(N, Lq, d)
+        o = F.linear(o, P["wo"], P["bo"])
+        m1 = _keep_mask(seed, (l << 2) | 1, N * Lq * d, p).view(N, Lq, d).to(x.device)
+        x = x + o * m1 * keep_scale
+        h = F.layer_norm(x, (d,), P["n2w"], P["n2b"], 1e-5)
+        f = F.relu(F.linear(h, P["w1"], P["b1"]))
+        m2 = _keep_mask(seed, (l << 2) | 2, N * Lq * f.shape[-1], p).view(N, Lq, -1).to(x.device)
+        f = F.linear(f * m2 * keep_scale, P["w2"], P["b2"])
+        m3 = _keep_mask(seed, (l << 2) | 3, N * Lq * d, p).view(N, Lq, d).to(x.device)
+        x = x + f * m3 * keep_scale
+    return x
+
+
+def test_decoder_stack_with_dropout_matches_torch_given_the_same_masks():
+    """vb_decoder_forward_train / vb_decoder_backward with dropout_p = 0.1 (attention probabilities, both sub-layer
+    outputs, FFN hidden) against the same layers in plain torch fed the masks of the documented hash: output and every
+    gradient within 1e-3 (fp32); the padded-batch key rule of the NAR training pass."""
+    from valle_b200 import _lib as L
+    from valle_b200 import autograd as AG
+    from valle_b200.modules.transformer import LayerNorm, TransformerEncoder, TransformerEncoderLayer
+    torch.manual_seed(4)
+    d, H, nl, N, Smax, Tmax, p, seed = 256, 4, 2, 3, 8, 40, 0.1, 987654321
+    enc = TransformerEncoder(TransformerEncoderLayer(d, H, dim_feedforward=4 * d, dropout=p, batch_first=True,
+                                                     norm_first=True), num_layers=nl, norm=LayerNorm(d)).to(DEV)
+    for q in enc.parameters():          # non-trivial biases / norm weights
+        if q.dim() == 1:
+            q.data.add_(torch.randn_like(q) * 0.05)
+    Lp = Smax + Tmax
+    xl = torch.tensor([8, 5, 3], dtype=torch.int32, device=DEV)
+    yl = torch.tensor([40, 29, 12], dtype=torch.int32, device=DEV)
+    x0 = torch.randn(N, Lp, d, device=DEV)
+    cu = (torch.arange(N + 1, dtype=torch.int32, device=DEV) * Lp).contiguous()
+    nd = enc.native(torch.float32)
+    params = AG.layer_params(enc)
+    xa = x0.clone().reshape(N * Lp, d).requires_grad_()
+    out = AG.DecoderStack.apply(xa, None, nd, (cu, N, Lp, L.VB_MASK_PADDED, xl, yl, Smax, p, seed), *params)
+    t = torch.arange(Lp, device=DEV)[None, :]
+    key_ok = (t < xl[:, None]) | ((t >= Smax) & (t < Smax + yl[:, None]))
+    w = torch.randn(N, Lp, d, device=DEV) * key_ok[..., None]              # padded rows carry no loss
+    (out.view(N, Lp, d) * w).sum().backward()
+    got = [q.grad.clone() for q in params] + [xa.grad.clone()]
+    for q in params:
+        q.grad = None
+    layers = []
+    for lyr in enc.layers:
+        layers.append(dict(wi=lyr.self_attn.in_proj_weight, bi=lyr.self_attn.in_proj_bias, wo=lyr.self_attn.out_proj.weight,
+                           bo=lyr.self_attn.out_proj.bias, w1=lyr.linear1.weight, b1=lyr.linear1.bias, w2=lyr.linear2.weight,
+                           b2=lyr.linear2.bias, n1w=lyr.norm1.weight, n1b=lyr.norm1.bias, n2w=lyr.norm2.weight,
+                           n2b=lyr.norm2.bias))
+    xr = x0.clone().requires_grad_()
+    ref = _torch_stack_with_masks(xr, layers, key_ok, p, seed, H)
+    (ref * w).sum().backward()
+    valid = key_ok[..., None].expand_as(ref)
+    assert _rel(out.view(N, Lp, d)[valid].detach(), ref[valid].detach()) < 1e-3
+    want = [q.grad for q in params] + [xr.grad.reshape(N * Lp, d)]
+    for i, (a, b) in enumerate(zip(got, want)):
+        if i == len(got) - 1:             # input gradient: valid rows only (padded rows see only masked keys)
+            a, b = a.view(N, Lp, d)[valid], b.view(N, Lp, d)[valid]
+        assert _rel(a, b) < 1e-3, (i, _rel(a, b))
+    # dropout really happened: the p = 0 result differs
+    out0 = AG.DecoderStack.apply(x0.clone().reshape(N * Lp, d), None, nd, (cu, N, Lp, L.VB_MASK_PADDED, xl, yl, Smax), *params)
+    assert _rel(out0.view(N, Lp, d)[valid].detach(), ref[valid].detach()) > 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_training_mode_applies_dropout_reproducibly(dtype):
+    """model.train() with the reference's default rates (0.1): the loss differs from the evaluation loss, repeats
+    under the same torch.manual_seed (the mask seed comes from the device generator), changes with another seed, and
+    loss.backward() yields finite gradients for every trainable parameter."""
+    g = load_golden("config0.pt")
+    fw = g["forward"]
+    m = build_model(g["config"], g["weight_seed"]).to(DEV)
+    m.engine_dtype = dtype
+    args = (fw["x"].to(DEV), fw["x_lens"], fw["y"].long().to(DEV), fw["y_lens"])
+
+    def run(seed, train=True):
+        m.train(train)
+        m.rng = random.Random(0)
+        torch.manual_seed(seed)
+        return m(*args, train_stage=0)[1]
+
+    with torch.no_grad():
+        le = float(run(5, train=False))
+    l1 = run(5)
+    l2 = float(run(5))
+    l3 = float(run(6))
+    assert float(l1) == l2 and l2 != l3
+    assert abs(float(l1) - le) > 1e-3 * abs(le) and abs(float(l1) - le) < 0.5 * abs(le)
+    for q in m.parameters():
+        q.grad = None
+    l1.backward()
+    for n, q in m.named_parameters():
+        if q.requires_grad:
+            assert q.grad is not None and torch.isfinite(q.grad).all(), n

@@ -16,8 +16,6 @@ if len(sys.argv) > 4 and sys.argv[4] == "ar_only":
     model.num_quantizers_saved = model.num_quantizers
 eng = model.engine(dtype)
 eng.quiet = True
-if os.environ.get('VB_MICRO'):
-    eng.micro_batches = int(os.environ['VB_MICRO'])
 if os.environ.get('VB_NO_GRAPH'):
     eng.use_cuda_graph = False
 texts, prompts = bench.make_batch(B, 0, dev)

@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvalle_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 VB_F32, VB_BF16 = 0, 1
 VB_EPI_NONE, VB_EPI_RELU, VB_EPI_RESIDUAL = 0, 1, 2
 VB_MASK_FULL, VB_MASK_VALLE_AR, VB_MASK_PADDED_AR, VB_MASK_PADDED, VB_MASK_DENSE = 0, 1, 2, 3, 4
@@ -96,10 +96,12 @@ PROTOTYPES = {
                                      C.c_int64, C.c_int64, C.c_int, vp, C.c_size_t, vp]),
     "vb_decoder_train_save_bytes": (C.c_size_t, [C.POINTER(DecoderDesc), C.c_int64]),
     "vb_decoder_forward_train": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp,
-                                           C.c_size_t, vp]),
+                                           C.c_size_t, C.c_float, C.c_uint64, vp]),
+    "vb_dropout": (C.c_int, [vp, vp, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, vp]),
     "vb_decoder_backward_workspace": (C.c_size_t, [C.POINTER(DecoderDesc), C.c_int64]),
     "vb_decoder_backward": (C.c_int, [vp, vp, C.c_int64, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp,
-                                      C.POINTER(LayerWt), C.POINTER(LayerGrads), vp, C.c_size_t, vp]),
+                                      C.POINTER(LayerWt), C.POINTER(LayerGrads), vp, C.c_size_t, C.c_float, C.c_uint64,
+                                      vp]),
     "vb_layernorm_backward": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, vp, vp, vp, C.c_float, vp, C.c_int64, vp,
                                         C.c_int64, vp, C.c_int, vp, vp, vp, vp]),
     "vb_cross_entropy_backward": (C.c_int, [vp, C.c_int64, vp, C.c_int64, C.c_int, C.c_int64, vp, C.c_float, vp, C.c_int,

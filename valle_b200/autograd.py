@@ -223,7 +223,8 @@ class DecoderStack(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, ada, nd, geom, *params):
-        cu, B, max_len, mode, tl, seg1, seg1_start = geom
+        cu, B, max_len, mode, tl, seg1, seg1_start = geom[:7]
+        drop_p, drop_seed = (geom[7], geom[8]) if len(geom) > 7 else (0.0, 0)   # training-mode dropout of the layers
         lib = L.load()
         x = x.detach().clone().contiguous()
         M = x.shape[0]
@@ -231,16 +232,18 @@ class DecoderStack(torch.autograd.Function):
             nb = lib.vb_decoder_train_save_bytes(C.byref(nd.desc), M)
             save = torch.empty(nb, dtype=torch.uint8, device=x.device)
             L.check(lib.vb_decoder_forward_train(nd.handle, x.data_ptr(), M, B, cu.data_ptr(), L.ptr(tl), L.ptr(seg1),
-                                                 seg1_start, max_len, mode, L.ptr(ada), save.data_ptr(), nb, _s()),
+                                                 seg1_start, max_len, mode, L.ptr(ada), save.data_ptr(), nb,
+                                                 float(drop_p), int(drop_seed), _s()),
                     "vb_decoder_forward_train")
         ctx.nd, ctx.geom, ctx.save = nd, geom, save
+        ctx.drop = (float(drop_p), int(drop_seed))
         ctx.ada = ada.detach() if ada is not None else None
         ctx.shapes = [tuple(p.shape) for p in params]
         return x
 
     @staticmethod
     def backward(ctx, dy):
-        nd, (cu, B, max_len, mode, tl, seg1, seg1_start) = ctx.nd, ctx.geom
+        nd, (cu, B, max_len, mode, tl, seg1, seg1_start) = ctx.nd, ctx.geom[:7]
         lib = L.load()
         dev = dy.device
         dx = dy.detach().to(torch.float32).clone().contiguous()
@@ -257,6 +260,32 @@ class DecoderStack(torch.autograd.Function):
             ws = torch.empty(nb, dtype=torch.uint8, device=dev)
             L.check(lib.vb_decoder_backward(nd.handle, dx.data_ptr(), M, B, cu.data_ptr(), L.ptr(tl), L.ptr(seg1),
                                             seg1_start, max_len, mode, L.ptr(ctx.ada), L.ptr(dada), ctx.save.data_ptr(),
-                                            wt, garr, ws.data_ptr(), nb, _s()), "vb_decoder_backward")
+                                            wt, garr, ws.data_ptr(), nb, ctx.drop[0], ctx.drop[1], _s()),
+                    "vb_decoder_backward")
         ctx.save = None
         return (dx, dada, None, None, *grads)
+
+
+class Dropout(torch.autograd.Function):
+    """nn.Dropout after the positional encoding (valle/modules/embedding.py:97) on the library's stateless mask:
+    vb_dropout forward, the same call on the gradient backward."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, stream_id):
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            L.check(L.load().vb_dropout(x.data_ptr(), out.data_ptr(), _DT[x.dtype], x.numel(), float(p), int(seed),
+                                        int(stream_id), _s()), "vb_dropout")
+        ctx.cfg = (float(p), int(seed), int(stream_id))
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        p, seed, sid = ctx.cfg
+        with torch.cuda.device(dy.device):
+            L.check(L.load().vb_dropout(dy.data_ptr(), dx.data_ptr(), _DT[dy.dtype], dy.numel(), p, seed, sid, _s()),
+                    "vb_dropout")
+        return dx, None, None, None

@@ -222,20 +222,24 @@ LayerSave carve_layer_save(const vb_decoder_desc &D, int64_t M, char *base) {
 }  // namespace
 
 VB_API size_t vb_decoder_train_save_bytes(const vb_decoder_desc *desc, int64_t M) {
-  return (size_t)desc->n_layer * layer_save_bytes(*desc, M) + 256;
+  // + one fp32 [M, d] scratch behind the layers: the sub-layer output that dropout scales before the residual add
+  return (size_t)desc->n_layer * layer_save_bytes(*desc, M) + align_up((size_t)M * desc->d_model * 4, 256) + 256;
 }
 
 VB_API int vb_decoder_forward_train(vb_decoder_t dec, float *x, int64_t M, int B, const int32_t *cu_seqlens,
                                     const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
                                     int mask_mode, const float *ada_wb, void *save, size_t save_bytes,
-                                    vb_stream_t stream) {
+                                    float dropout_p, uint64_t dropout_seed, vb_stream_t stream) {
   VB_CHECK_ARG(dec && x && cu_seqlens && save, "vb_decoder_forward_train: null argument");
+  VB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "vb_decoder_forward_train: dropout_p=%g not in [0, 1)", (double)dropout_p);
   const vb_decoder_desc &D = dec->desc;
   VB_CHECK_ARG(save_bytes >= vb_decoder_train_save_bytes(&D, M), "vb_decoder_forward_train: save buffer too small");
   if (M == 0) return VB_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int d = D.d_model, dff = D.d_ff, dt = D.wdtype;
   const size_t per_layer = layer_save_bytes(D, M);
+  const bool drop = dropout_p > 0.f;
+  float *sub = (float *)((char *)save + (size_t)D.n_layer * per_layer);   // sub-layer output ahead of its dropout
   for (int l = 0; l < D.n_layer; ++l) {
     const vb_layer_params &P = dec->layers[l];
     LayerSave sv = carve_layer_save(D, M, (char *)save + (size_t)l * per_layer);
@@ -245,14 +249,30 @@ VB_API int vb_decoder_forward_train(vb_decoder_t dec, float *x, int64_t M, int B
     VB_TRY(vb_layernorm(x, d, nullptr, M, d, P.norm1_w, P.norm1_b, ada1, 1e-5f, sv.xn1, dt, stream));
     VB_TRY(vb_linear(sv.xn1, dt, d, P.in_proj_w, dt, P.in_proj_b, sv.qkv, dt, 3 * d, M, 3 * d, d, VB_EPI_NONE, nullptr, 0,
                      stream));
+    // training-mode dropout (p > 0): attention probabilities (activation.py:199 `dropout=`), dropout1 / dropout2 on
+    // the sub-layer outputs and `dropout` on the FFN hidden (transformer.py:329,333-334); masks from the stateless
+    // hash of kernels.cuh, site streams (l << 2) | {0, 1, 2, 3}, regenerated by vb_decoder_backward
+    const DropCfg dc_attn = make_drop(dropout_p, dropout_seed, (uint32_t)(l << 2) | 0u);
     VB_TRY(launch_attention_varlen(sv.qkv, dt, M, B, D.n_head, d / D.n_head, cu_seqlens, text_lens, seg1_lens, seg1_start,
-                                   max_seqlen, mask_mode, sv.att, nullptr, nullptr, 0, 0, nullptr, 0, s));
-    VB_TRY(vb_linear(sv.att, dt, d, P.out_proj_w, dt, P.out_proj_b, x, VB_F32, d, M, d, d, VB_EPI_RESIDUAL, nullptr, 0,
-                     stream));
+                                   max_seqlen, mask_mode, sv.att, nullptr, nullptr, 0, 0, nullptr, 0, s, &dc_attn));
+    if (drop) {
+      VB_TRY(vb_linear(sv.att, dt, d, P.out_proj_w, dt, P.out_proj_b, sub, VB_F32, d, M, d, d, VB_EPI_NONE, nullptr, 0,
+                       stream));
+      VB_TRY(launch_dropout_add(x, sub, (int64_t)M * d, make_drop(dropout_p, dropout_seed, (uint32_t)(l << 2) | 1u), s));
+    } else {
+      VB_TRY(vb_linear(sv.att, dt, d, P.out_proj_w, dt, P.out_proj_b, x, VB_F32, d, M, d, d, VB_EPI_RESIDUAL, nullptr, 0,
+                       stream));
+    }
     VB_CUDA(cudaMemcpyAsync(sv.x_mid, x, (size_t)M * d * 4, cudaMemcpyDeviceToDevice, s));
     VB_TRY(vb_layernorm(x, d, nullptr, M, d, P.norm2_w, P.norm2_b, ada2, 1e-5f, sv.xn2, dt, stream));
     VB_TRY(vb_linear(sv.xn2, dt, d, P.lin1_w, dt, P.lin1_b, sv.hb, dt, dff, M, dff, d, VB_EPI_RELU, nullptr, 0, stream));
-    VB_TRY(vb_linear(sv.hb, dt, dff, P.lin2_w, dt, P.lin2_b, x, VB_F32, d, M, d, dff, VB_EPI_RESIDUAL, nullptr, 0, stream));
+    if (drop) {
+      VB_TRY(launch_dropout(sv.hb, sv.hb, dt, (int64_t)M * dff, make_drop(dropout_p, dropout_seed, (uint32_t)(l << 2) | 2u), s));
+      VB_TRY(vb_linear(sv.hb, dt, dff, P.lin2_w, dt, P.lin2_b, sub, VB_F32, d, M, d, dff, VB_EPI_NONE, nullptr, 0, stream));
+      VB_TRY(launch_dropout_add(x, sub, (int64_t)M * d, make_drop(dropout_p, dropout_seed, (uint32_t)(l << 2) | 3u), s));
+    } else {
+      VB_TRY(vb_linear(sv.hb, dt, dff, P.lin2_w, dt, P.lin2_b, x, VB_F32, d, M, d, dff, VB_EPI_RESIDUAL, nullptr, 0, stream));
+    }
   }
   return VB_OK;
 }
@@ -261,6 +281,7 @@ VB_API size_t vb_decoder_backward_workspace(const vb_decoder_desc *desc, int64_t
   const size_t ts = elem_size(desc->wdtype), d = desc->d_model, dff = desc->d_ff, Mp = align_up((size_t)M, 128);
   size_t n = 0;
   n += align_up(Mp * d * ts, 256);        // dx in the storage dtype
+  n += align_up(Mp * d * ts, 256);        // dy: dx through the mask of a sub-layer's output dropout
   n += align_up(Mp * dff * ts, 256);      // dh
   n += align_up(Mp * d * 4, 256);         // dc / da (fp32)
   n += align_up(Mp * d * ts, 256);        // do
@@ -274,8 +295,9 @@ VB_API int vb_decoder_backward(vb_decoder_t dec, float *dx, int64_t M, int B, co
                                const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
                                int mask_mode, const float *ada_wb, float *dada_wb, const void *save,
                                const vb_layer_wt *wt, const vb_layer_grads *grads, void *workspace,
-                               size_t workspace_bytes, vb_stream_t stream) {
+                               size_t workspace_bytes, float dropout_p, uint64_t dropout_seed, vb_stream_t stream) {
   VB_CHECK_ARG(dec && dx && cu_seqlens && save && wt && grads, "vb_decoder_backward: null argument");
+  VB_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "vb_decoder_backward: dropout_p=%g not in [0, 1)", (double)dropout_p);
   const vb_decoder_desc &D = dec->desc;
   VB_CHECK_ARG(workspace_bytes >= vb_decoder_backward_workspace(&D, M), "vb_decoder_backward: workspace too small");
   VB_CHECK_ARG(!ada_wb || dada_wb, "vb_decoder_backward: AdaLN stack needs dada_wb");
@@ -290,7 +312,10 @@ VB_API int vb_decoder_backward(vb_decoder_t dec, float *dx, int64_t M, int B, co
     return r;
   };
   void *dx_dt = take(Mp * d * ts);
+  void *dy = take(Mp * d * ts);
   void *dh = take(Mp * dff * ts);
+  const bool drop = dropout_p > 0.f;
+  const float inv_keep = drop ? 1.f / (1.f - dropout_p) : 1.f;
   float *dn = (float *)take(Mp * d * 4);
   void *dO = take(Mp * d * ts);
   void *dqkv = take(Mp * 3 * d * ts);
@@ -310,18 +335,31 @@ VB_API int vb_decoder_backward(vb_decoder_t dec, float *dx, int64_t M, int B, co
     float *dada1 = dada_wb ? dada_wb + (size_t)(2 * l) * 2 * d : nullptr;
     float *dada2 = dada_wb ? dada_wb + (size_t)(2 * l + 1) * 2 * d : nullptr;
     // ---- FFN: x2 = x1 + relu(LN2(x1) W1^T + b1) W2^T + b2 (transformer.py:332-334) ----
-    VB_TRY(vb_linear_backward(sv.hb, dt, dff, T.lin2_wt, dx_dt, d, dh, dt, dff, VB_EPI_NONE, G.lin2_w, G.lin2_b, M, d, dff,
+    // (with dropout: the saved hidden is post-dropout -- zero where dropped -- and dx reaches the sub-layer output
+    //  through the mask of dropout2)
+    const void *dy2 = dx_dt;
+    if (drop) {
+      VB_TRY(launch_dropout(dx_dt, dy, dt, (int64_t)M * d, make_drop(dropout_p, dropout_seed, (uint32_t)(l << 2) | 3u), s));
+      dy2 = dy;
+    }
+    VB_TRY(vb_linear_backward(sv.hb, dt, dff, T.lin2_wt, dy2, d, dh, dt, dff, VB_EPI_NONE, G.lin2_w, G.lin2_b, M, d, dff,
                               lin_ws, lin_ws_bytes, stream));
-    VB_TRY(launch_relu_bwd(dh, sv.hb, dt, (int64_t)M * dff, s));
+    VB_TRY(launch_relu_bwd(dh, sv.hb, dt, (int64_t)M * dff, inv_keep, s));
     VB_TRY(vb_linear_backward(sv.xn2, dt, d, T.lin1_wt, dh, dff, dn, VB_F32, d, VB_EPI_NONE, G.lin1_w, G.lin1_b, M, dff, d,
                               lin_ws, lin_ws_bytes, stream));
     VB_TRY(vb_layernorm_backward(sv.x_mid, d, nullptr, M, d, P.norm2_w, P.norm2_b, ada2, 1e-5f, dn, d, dx, d, dx_dt, dt,
                                  G.norm2_w, G.norm2_b, dada2, stream));
     // ---- attention block: x1 = x + Attn(LN1(x) Win^T + bin) Wo^T + bo (transformer.py:315-330) ----
-    VB_TRY(vb_linear_backward(sv.att, dt, d, T.out_proj_wt, dx_dt, d, dO, dt, d, VB_EPI_NONE, G.out_proj_w, G.out_proj_b, M, d,
+    const void *dy1 = dx_dt;
+    if (drop) {
+      VB_TRY(launch_dropout(dx_dt, dy, dt, (int64_t)M * d, make_drop(dropout_p, dropout_seed, (uint32_t)(l << 2) | 1u), s));
+      dy1 = dy;
+    }
+    VB_TRY(vb_linear_backward(sv.att, dt, d, T.out_proj_wt, dy1, d, dO, dt, d, VB_EPI_NONE, G.out_proj_w, G.out_proj_b, M, d,
                               d, lin_ws, lin_ws_bytes, stream));
-    VB_TRY(vb_attention_backward(sv.qkv, sv.att, dO, dt, M, B, D.n_head, d / D.n_head, cu_seqlens, text_lens, seg1_lens,
-                                 seg1_start, max_seqlen, mask_mode, dqkv, attn_ws, attn_ws_bytes, stream));
+    const DropCfg dc_attn = make_drop(dropout_p, dropout_seed, (uint32_t)(l << 2) | 0u);
+    VB_TRY(attention_backward(sv.qkv, sv.att, dO, dt, M, B, D.n_head, d / D.n_head, cu_seqlens, text_lens, seg1_lens,
+                              seg1_start, max_seqlen, mask_mode, dqkv, attn_ws, attn_ws_bytes, &dc_attn, s));
     VB_TRY(vb_linear_backward(sv.xn1, dt, d, T.in_proj_wt, dqkv, 3 * d, dn, VB_F32, d, VB_EPI_NONE, G.in_proj_w, G.in_proj_b,
                               M, 3 * d, d, lin_ws, lin_ws_bytes, stream));
     VB_TRY(vb_layernorm_backward(sv.x_in, d, nullptr, M, d, P.norm1_w, P.norm1_b, ada1, 1e-5f, dn, d, dx, d, dx_dt, dt,

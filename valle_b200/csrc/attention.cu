@@ -26,7 +26,7 @@ attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__
                         const int32_t *__restrict__ text_lens, const int32_t *__restrict__ seg1_lens,
                         int seg1_start, int mask_mode, T *__restrict__ out,
                         T *__restrict__ kcache, T *__restrict__ vcache, int64_t cache_seq_stride,
-                        int cache_cap, const uint8_t *__restrict__ dmask, int64_t dld) {
+                        int cache_cap, const uint8_t *__restrict__ dmask, int64_t dld, DropCfg drop) {
   constexpr int LDT = 68;  // padded leading dim (floats), keeps float4 alignment
   extern __shared__ __align__(16) float smem[];
   float *Qt = smem;             // [64 e][LDT rows]
@@ -141,6 +141,11 @@ attn_varlen_simt_kernel(const T *__restrict__ qkv, int n_head, const int32_t *__
       m_run[i] = m_new;
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[i][j] *= corr;
+      if (drop.thresh != 0) {   // training: dropout on the normalised probabilities = on p~ with the full row sum kept
+        const uint64_t base = ((uint64_t)(b * n_head + h) * drop.lmax + (q0 + ty * 4 + i)) * drop.lmax + j0 + tx * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = drop_keep(drop, base + j) ? s[i][j] * drop.inv_keep : 0.f;
+      }
     }
     // P^T to shared: Pt[key][row]
 #pragma unroll
@@ -176,8 +181,12 @@ int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_
                             const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,
                             int seg1_start, int max_seqlen, int mask_mode, void *out, void *kcache, void *vcache,
                             int64_t cache_seq_stride, int cache_cap, const uint8_t *dense_mask, int64_t dense_ld,
-                            cudaStream_t s) {
+                            cudaStream_t s, const DropCfg *drop) {
   VB_CHECK_ARG(head_dim == HD, "attention: head_dim=%d, only 64 is built", head_dim);
+  DropCfg dc{};
+  if (drop) dc = *drop;
+  dc.lmax = max_seqlen;
+  const bool dropping = dc.thresh != 0;   // attention-probability dropout: the CUDA-core kernel carries the mask
   VB_CHECK_ARG(mask_mode >= VB_MASK_FULL && mask_mode <= VB_MASK_DENSE, "attention: bad mask mode %d", mask_mode);
   if (mask_mode == VB_MASK_DENSE) {
     VB_CHECK_ARG(dense_mask != nullptr && dense_ld >= max_seqlen, "attention: VB_MASK_DENSE needs a [>=L, >=L] byte mask");
@@ -194,21 +203,21 @@ int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_
     auto k = attn_varlen_simt_kernel<float>;
     VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, 256, smem, s>>>((const float *)qkv, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, (float *)out,
-                              (float *)kcache, (float *)vcache, cache_seq_stride, cache_cap, dense_mask, dense_ld);
-  } else if (dtype == VB_BF16 && dense_mask == nullptr && kcache == nullptr && getenv("VB_ATTN_SIMT") == nullptr &&
+                              (float *)kcache, (float *)vcache, cache_seq_stride, cache_cap, dense_mask, dense_ld, dc);
+  } else if (dtype == VB_BF16 && !dropping && dense_mask == nullptr && kcache == nullptr && getenv("VB_ATTN_SIMT") == nullptr &&
              attention_tcgen05_enabled()) {
     // 128-row query tiles on tcgen05/TMEM; a ragged last tile is shifted back to [L-128, L) (overlap, rows are
     // independent) so that a length like 1025 costs 9 tiles, not 9 tiles plus a 64-row warp-level pass
     return launch_attention_tcgen05((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start,
                                     max_seqlen, mask_mode, (bf16 *)out, 2, s);
-  } else if (dtype == VB_BF16 && dense_mask == nullptr && getenv("VB_ATTN_SIMT") == nullptr) {
+  } else if (dtype == VB_BF16 && !dropping && dense_mask == nullptr && getenv("VB_ATTN_SIMT") == nullptr) {
     return launch_attention_mma((const bf16 *)qkv, M, B, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, max_seqlen, mask_mode,
                                 (bf16 *)out, (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, 0, s);
   } else if (dtype == VB_BF16) {
     auto k = attn_varlen_simt_kernel<bf16>;
     VB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, 256, smem, s>>>((const bf16 *)qkv, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start, mask_mode, (bf16 *)out,
-                              (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, dense_mask, dense_ld);
+                              (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, dense_mask, dense_ld, dc);
   } else {
     set_error("attention: bad dtype %d", dtype);
     return VB_ERR_ARG;

@@ -61,11 +61,24 @@ __global__ void colsum_kernel(const T *__restrict__ in, int64_t ld, int64_t R, i
   }
 }
 
-// ---- dh = (h > 0) ? dh : 0 ------------------------------------------------------------------------------------
+// ---- dh = (h > 0) ? dh * scale : 0   (scale = 1 / keep when h went through dropout: dropped entries are 0 in h) ------
 template <typename T>
-__global__ void relu_bwd_kernel(T *__restrict__ dh, const T *__restrict__ h, int64_t n) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+__global__ void relu_bwd_kernel(T *__restrict__ dh, const T *__restrict__ h, int64_t n, float scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     if (!(to_f32(h[i]) > 0.f)) dh[i] = from_f32<T>(0.f);
+    else if (scale != 1.f) dh[i] = from_f32<T>(to_f32(dh[i]) * scale);
+  }
+}
+
+// ---- dropout (element index = linear offset into the contiguous tensor) ------------------------------------------
+template <typename T>
+__global__ void dropout_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t n, DropCfg cfg) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = drop_keep(cfg, (uint64_t)i) ? from_f32<T>(to_f32(in[i]) * cfg.inv_keep) : from_f32<T>(0.f);
+}
+__global__ void dropout_add_kernel(float *__restrict__ x, const float *__restrict__ t, int64_t n, DropCfg cfg) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    if (drop_keep(cfg, (uint64_t)i)) x[i] += t[i] * cfg.inv_keep;
 }
 
 // ---- LayerNorm / AdaptiveLayerNorm backward --------------------------------------------------------------------
@@ -264,7 +277,7 @@ __global__ void __launch_bounds__(256)
 attn_bwd_dq_kernel(const T *__restrict__ qkv, const T *__restrict__ o, const T *__restrict__ dout, int n_head,
                    const int32_t *__restrict__ cu_seqlens, const int32_t *__restrict__ text_lens,
                    const int32_t *__restrict__ seg1_lens, int seg1_start, int mask_mode, T *__restrict__ dqkv,
-                   float *__restrict__ lse_out, float *__restrict__ dsum_out) {
+                   float *__restrict__ lse_out, float *__restrict__ dsum_out, DropCfg drop) {
   extern __shared__ __align__(16) float smem[];
   float *Qt = smem;              // [e][q]
   float *dOt = Qt + 64 * LDT;    // [e][q]
@@ -361,10 +374,13 @@ attn_bwd_dq_kernel(const T *__restrict__ qkv, const T *__restrict__ o, const T *
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float lse = s_lse[ty * 4 + i], Dv = s_D[ty * 4 + i];
+      const uint64_t base = ((uint64_t)(b * n_head + h) * drop.lmax + (q0 + ty * 4 + i)) * drop.lmax + j0 + tx * 4;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float p = lim[i].ok(j0 + tx * 4 + j) ? expf(s[i][j] * 0.125f - lse) : 0.f;
-        dSt[(tx * 4 + j) * LDT + ty * 4 + i] = p * (dp[i][j] - Dv);
+        float dpm = dp[i][j];   // with dropout O = (m / keep o P) V: dP reaches P through the same mask
+        if (drop.thresh != 0) dpm = drop_keep(drop, base + j) ? dpm * drop.inv_keep : 0.f;
+        dSt[(tx * 4 + j) * LDT + ty * 4 + i] = p * (dpm - Dv);
       }
     }
     __syncthreads();
@@ -396,7 +412,7 @@ __global__ void __launch_bounds__(256)
 attn_bwd_dkv_kernel(const T *__restrict__ qkv, const T *__restrict__ dout, int n_head,
                     const int32_t *__restrict__ cu_seqlens, const int32_t *__restrict__ text_lens,
                     const int32_t *__restrict__ seg1_lens, int seg1_start, int mask_mode, T *__restrict__ dqkv,
-                    const float *__restrict__ lse_in, const float *__restrict__ dsum_in) {
+                    const float *__restrict__ lse_in, const float *__restrict__ dsum_in, DropCfg drop) {
   extern __shared__ __align__(16) float smem[];
   float *Kt = smem;              // [e][key]
   float *Vt = Kt + 64 * LDT;     // [e][key]
@@ -441,11 +457,18 @@ attn_bwd_dkv_kernel(const T *__restrict__ qkv, const T *__restrict__ dout, int n
       const int qr = q0 + ty * 4 + i;
       const RowMask lim = make_row_mask(mask_mode, qr, L, S, seg1_start, c1);
       const float lse = s_lse[ty * 4 + i], Dv = s_D[ty * 4 + i];
+      const uint64_t base = ((uint64_t)(b * n_head + h) * drop.lmax + qr) * drop.lmax + k0 + tx * 4;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float p = lim.ok(k0 + tx * 4 + j) ? expf(s[i][j] * 0.125f - lse) : 0.f;
-        Pt[(ty * 4 + i) * LDT + tx * 4 + j] = p;
-        dSt[(ty * 4 + i) * LDT + tx * 4 + j] = p * (dp[i][j] - Dv);
+        float pm = p, dpm = dp[i][j];
+        if (drop.thresh != 0) {
+          const float mk = drop_keep(drop, base + j) ? drop.inv_keep : 0.f;
+          pm *= mk;
+          dpm *= mk;
+        }
+        Pt[(ty * 4 + i) * LDT + tx * 4 + j] = pm;               // dV = (m / keep o P)^T dO
+        dSt[(ty * 4 + i) * LDT + tx * 4 + j] = p * (dpm - Dv);
       }
     }
     __syncthreads();
@@ -526,13 +549,32 @@ int launch_colsum(const void *in, int dtype, int64_t ld, int64_t R, int N, float
   return VB_OK;
 }
 
-int launch_relu_bwd(void *dh, const void *h, int dtype, int64_t n, cudaStream_t s) {
+int launch_dropout(const void *in, void *out, int dtype, int64_t n, const DropCfg &cfg, cudaStream_t s) {
   if (n == 0) return VB_OK;
   const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
   if (dtype == VB_F32)
-    bw::relu_bwd_kernel<float><<<grid, 256, 0, s>>>((float *)dh, (const float *)h, n);
+    bw::dropout_kernel<float><<<grid, 256, 0, s>>>((const float *)in, (float *)out, n, cfg);
   else
-    bw::relu_bwd_kernel<bf16><<<grid, 256, 0, s>>>((bf16 *)dh, (const bf16 *)h, n);
+    bw::dropout_kernel<bf16><<<grid, 256, 0, s>>>((const bf16 *)in, (bf16 *)out, n, cfg);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+int launch_dropout_add(float *x, const float *t, int64_t n, const DropCfg &cfg, cudaStream_t s) {
+  if (n == 0) return VB_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  bw::dropout_add_kernel<<<grid, 256, 0, s>>>(x, t, n, cfg);
+  VB_LAUNCH_CHECK();
+  return VB_OK;
+}
+
+int launch_relu_bwd(void *dh, const void *h, int dtype, int64_t n, float scale, cudaStream_t s) {
+  if (n == 0) return VB_OK;
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+  if (dtype == VB_F32)
+    bw::relu_bwd_kernel<float><<<grid, 256, 0, s>>>((float *)dh, (const float *)h, n, scale);
+  else
+    bw::relu_bwd_kernel<bf16><<<grid, 256, 0, s>>>((bf16 *)dh, (const bf16 *)h, n, scale);
   VB_LAUNCH_CHECK();
   return VB_OK;
 }
@@ -656,12 +698,34 @@ VB_API int vb_linear_backward(const void *X, int dtype, int64_t ldx, const void 
   return VB_OK;
 }
 
+VB_API int vb_dropout(const void *in, void *out, int dtype, int64_t n, float p, uint64_t seed, uint32_t stream_id,
+                      vb_stream_t stream) {
+  VB_CHECK_ARG(in && out && (dtype == VB_F32 || dtype == VB_BF16), "vb_dropout: bad argument");
+  VB_CHECK_ARG(p >= 0.f && p < 1.f, "vb_dropout: p=%g not in [0, 1)", (double)p);
+  if (p == 0.f) {
+    if (in != out) VB_CUDA(cudaMemcpyAsync(out, in, (size_t)n * (dtype == VB_F32 ? 4 : 2), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return VB_OK;
+  }
+  return launch_dropout(in, out, dtype, n, make_drop(p, seed, stream_id), (cudaStream_t)stream);
+}
+
 VB_API size_t vb_attention_backward_workspace(int64_t M, int n_head) { return (size_t)M * n_head * 2 * sizeof(float) + 256; }
 
 VB_API int vb_attention_backward(const void *qkv, const void *out, const void *dout, int dtype, int64_t M, int B,
                                  int n_head, int head_dim, const int32_t *cu_seqlens, const int32_t *text_lens,
                                  const int32_t *seg1_lens, int seg1_start, int max_seqlen, int mask_mode, void *dqkv,
                                  void *workspace, size_t workspace_bytes, vb_stream_t stream) {
+  return vb::attention_backward(qkv, out, dout, dtype, M, B, n_head, head_dim, cu_seqlens, text_lens, seg1_lens, seg1_start,
+                                max_seqlen, mask_mode, dqkv, workspace, workspace_bytes, nullptr, (cudaStream_t)stream);
+}
+
+int vb::attention_backward(const void *qkv, const void *out, const void *dout, int dtype, int64_t M, int B, int n_head,
+                           int head_dim, const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,
+                           int seg1_start, int max_seqlen, int mask_mode, void *dqkv, void *workspace,
+                           size_t workspace_bytes, const DropCfg *drop, cudaStream_t s) {
+  DropCfg dc{};
+  if (drop) dc = *drop;
+  dc.lmax = max_seqlen;
   VB_CHECK_ARG(head_dim == bw::HD, "vb_attention_backward: head_dim=%d, only 64 is built", head_dim);
   VB_CHECK_ARG(mask_mode >= VB_MASK_FULL && mask_mode <= VB_MASK_PADDED, "vb_attention_backward: bad mask mode");
   VB_CHECK_ARG(mask_mode == VB_MASK_FULL || text_lens != nullptr, "vb_attention_backward: this mask mode needs text_lens");
@@ -669,7 +733,6 @@ VB_API int vb_attention_backward(const void *qkv, const void *out, const void *d
   VB_CHECK_ARG(workspace && workspace_bytes >= vb_attention_backward_workspace(M, n_head),
                "vb_attention_backward: workspace too small");
   if (M == 0 || B == 0) return VB_OK;
-  cudaStream_t s = (cudaStream_t)stream;
   float *lse = (float *)workspace;
   float *dsum = lse + (size_t)M * n_head;
   dim3 grid((max_seqlen + 63) / 64, n_head, B);
@@ -680,10 +743,10 @@ VB_API int vb_attention_backward(const void *qkv, const void *out, const void *d
     VB_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
     VB_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
     kq<<<grid, 256, smem_q, s>>>((const float *)qkv, (const float *)out, (const float *)dout, n_head, cu_seqlens, text_lens,
-                                 seg1_lens, seg1_start, mask_mode, (float *)dqkv, lse, dsum);
+                                 seg1_lens, seg1_start, mask_mode, (float *)dqkv, lse, dsum, dc);
     VB_LAUNCH_CHECK();
     kk<<<grid, 256, smem_k, s>>>((const float *)qkv, (const float *)dout, n_head, cu_seqlens, text_lens, seg1_lens,
-                                 seg1_start, mask_mode, (float *)dqkv, lse, dsum);
+                                 seg1_start, mask_mode, (float *)dqkv, lse, dsum, dc);
     VB_LAUNCH_CHECK();
   } else if (dtype == VB_BF16) {
     auto kq = bw::attn_bwd_dq_kernel<bf16>;
@@ -691,10 +754,10 @@ VB_API int vb_attention_backward(const void *qkv, const void *out, const void *d
     VB_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
     VB_CUDA(cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
     kq<<<grid, 256, smem_q, s>>>((const bf16 *)qkv, (const bf16 *)out, (const bf16 *)dout, n_head, cu_seqlens, text_lens,
-                                 seg1_lens, seg1_start, mask_mode, (bf16 *)dqkv, lse, dsum);
+                                 seg1_lens, seg1_start, mask_mode, (bf16 *)dqkv, lse, dsum, dc);
     VB_LAUNCH_CHECK();
     kk<<<grid, 256, smem_k, s>>>((const bf16 *)qkv, (const bf16 *)dout, n_head, cu_seqlens, text_lens, seg1_lens, seg1_start,
-                                 mask_mode, (bf16 *)dqkv, lse, dsum);
+                                 mask_mode, (bf16 *)dqkv, lse, dsum, dc);
     VB_LAUNCH_CHECK();
   } else {
     set_error("vb_attention_backward: bad dtype %d", dtype);

@@ -5,6 +5,39 @@
 namespace vb {
 
 // Visibility rule of one query row (see vb_mask_mode): key c is seen iff c < lim0 or s1 <= c < hi1.
+// Training-mode dropout (valle/modules/transformer.py:329,333-334, activation.py attention dropout, embedding.py:97):
+// a stateless Bernoulli mask keyed by (seed of the forward call, stream id of the site, element index), so the backward
+// pass regenerates the mask of the forward pass instead of storing it.  splitmix64 finaliser; keep <=> hash >= thresh
+// with thresh = p * 2^32.  tests/test_backward_gpu.py holds the same function in numpy.
+struct DropCfg {
+  uint64_t seed;
+  uint32_t stream;     // site id: (layer << 2) | {0 attention probabilities, 1 after out-proj, 2 FFN hidden, 3 after FFN}
+  uint32_t thresh;     // 0 = dropout off
+  float inv_keep;      // 1 / (1 - p)
+  int64_t lmax;        // attention only: index = ((b * H + h) * lmax + q) * lmax + k
+};
+__host__ __device__ __forceinline__ bool drop_keep(const DropCfg &c, uint64_t idx) {
+  uint64_t z = c.seed + (uint64_t)c.stream * 0x9E3779B97F4A7C15ull + idx * 0xD1342543DE82EF95ull;
+  z ^= z >> 30;
+  z *= 0xBF58476D1CE4E5B9ull;
+  z ^= z >> 27;
+  z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32) >= c.thresh;
+}
+inline DropCfg make_drop(float p, uint64_t seed, uint32_t stream, int64_t lmax = 0) {
+  DropCfg c{};
+  if (p > 0.f) {
+    c.seed = seed;
+    c.stream = stream;
+    const double t = (double)p * 4294967296.0;
+    c.thresh = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    c.inv_keep = 1.f / (1.f - p);
+    c.lmax = lmax;
+  }
+  return c;
+}
+
 struct RowMask {
   int lim0, s1, hi1;
   __device__ __forceinline__ bool ok(int c) const { return c < lim0 || (c >= s1 && c < hi1); }
@@ -110,7 +143,7 @@ int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_
                             const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,
                             int seg1_start, int max_seqlen, int mask_mode, void *out, void *kcache, void *vcache,
                             int64_t cache_seq_stride, int cache_cap, const uint8_t *dense_mask, int64_t dense_ld,
-                            cudaStream_t s);
+                            cudaStream_t s, const DropCfg *drop = nullptr);
 // attention_mma.cu (bf16 tensor-core flash attention)
 int launch_attention_mma(const bf16 *qkv, int64_t M, int B, int n_head, const int32_t *cu_seqlens,
                          const int32_t *text_lens, const int32_t *seg1_lens, int seg1_start, int max_seqlen,
@@ -139,7 +172,14 @@ int launch_ln_reduce(float *x, int64_t ldx, int B, int d, const float *partials,
 int launch_transpose_pad(const void *in, int dtype, int64_t ld_in, int64_t R, int C, void *out, int64_t ld_out,
                          cudaStream_t s);
 int launch_colsum(const void *in, int dtype, int64_t ld, int64_t R, int N, float *out, cudaStream_t s);
-int launch_relu_bwd(void *dh, const void *h, int dtype, int64_t n, cudaStream_t s);
+int launch_relu_bwd(void *dh, const void *h, int dtype, int64_t n, float scale, cudaStream_t s);
+int attention_backward(const void *qkv, const void *out, const void *dout, int dtype, int64_t M, int B, int n_head,
+                       int head_dim, const int32_t *cu_seqlens, const int32_t *text_lens, const int32_t *seg1_lens,
+                       int seg1_start, int max_seqlen, int mask_mode, void *dqkv, void *workspace, size_t workspace_bytes,
+                       const DropCfg *drop, cudaStream_t s);
+// out[i] = keep(i) ? in[i] / (1 - p) : 0 (in place allowed); x[i] += keep(i) ? t[i] / (1 - p) : 0
+int launch_dropout(const void *in, void *out, int dtype, int64_t n, const DropCfg &cfg, cudaStream_t s);
+int launch_dropout_add(float *x, const float *t, int64_t n, const DropCfg &cfg, cudaStream_t s);
 int launch_cast_from_f32(const float *in, void *out, int dtype, int64_t n, cudaStream_t s);
 
 // sample.cu

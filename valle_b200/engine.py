@@ -94,42 +94,7 @@ class _ArBuffers:
         nbytes = eng.lib.vb_ar_step_workspace(C.byref(nd.desc), B, cap)
         self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.views: List["_ArView"] = []
         self.eng = eng
-
-    def make_views(self, n: int) -> List["_ArView"]:
-        """Split the B rows into n contiguous micro-batches that decode concurrently on their own
-        streams: one micro-batch's latency-bound projection chain overlaps the other's HBM-bound
-        KV-cache attention.  The views alias this buffer's state arrays and KV cache."""
-        if len(self.views) != n:
-            base, rem = divmod(self.B, n)
-            self.views, b0 = [], 0
-            for i in range(n):
-                nb = base + (1 if i < rem else 0)
-                self.views.append(_ArView(self, b0, nb))
-                b0 += nb
-        return self.views
-
-
-class _ArView:
-    def __init__(self, buf: "_ArBuffers", b0: int, nb: int):
-        eng = buf.eng
-        self.b0, self.B = b0, nb
-        st = L.ArState()
-        st.B, st.tok_stride = nb, buf.tok_stride
-        st.text_len, st.prompt_len, st.max_new = (buf.text_len[b0:].data_ptr(), buf.prompt_len[b0:].data_ptr(),
-                                                  buf.max_new[b0:].data_ptr())
-        st.n_gen, st.finished, st.tokens = buf.n_gen[b0:].data_ptr(), buf.finished[b0:].data_ptr(), buf.tokens[b0:].data_ptr()
-        st.x_cur, st.logits = buf.x_cur[b0:].data_ptr(), buf.logits[b0:].data_ptr()
-        st.kcache, st.vcache = buf.kcache[:, b0:].data_ptr(), buf.vcache[:, b0:].data_ptr()
-        st.cache_layer_stride, st.cache_seq_stride, st.cache_cap = buf.kcache.stride(0), buf.kcache.stride(1), buf.cap
-        self.st = st
-        nbytes = eng.lib.vb_ar_step_workspace(C.byref(eng.ar.desc), nb, buf.cap)
-        self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=eng.device)
-        self.stream = torch.cuda.Stream(device=eng.device)
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.graph_key = None
-        self.graph_kernels = 0
 
 
 def _seg_ranges(starts, lens):
@@ -172,8 +137,6 @@ class ValleEngine:
         #: one utterance after the other), so that a fixed torch.manual_seed reproduces the reference's ids; the
         #: default draws on the device (torch.multinomial on CUDA logits, Philox stream) without a per-token sync
         self.sample_on_host = False
-        #: micro-batches decoded concurrently on separate streams when B >= 32 (bf16 tensor-core path)
-        self.micro_batches = 1
         self.last_packed: Optional[torch.Tensor] = None
         #: rows of one tensor-core decode group (gemm_decode.cu: one UMMA N tile); larger bf16 batches are split
         self.max_tc_batch = 64
@@ -426,7 +389,7 @@ class ValleEngine:
         steps = 0
         while steps < max_steps:
             n = min(poll, max_steps - steps)
-            if greedy and self.use_cuda_graph and not self._use_views(buf, greedy):
+            if greedy and self.use_cuda_graph:
                 # whole groups of `steps_per_graph` decode steps as one graph replay (no launch gap between the
                 # steps of a group), the remainder one step at a time
                 done = 0
@@ -441,7 +404,6 @@ class ValleEngine:
                         fs = forced_steps[min(steps + 1, forced_steps.shape[0] - 1)]
                     self._decode_step(buf, head, greedy, top_k, temperature, fs)
             steps += n
-            self._join_views(buf)
             if trace is not None and want(steps):  # poll == 1 here: the logits row of iteration `steps`
                 trace["ar_logits"][steps] = buf.logits[:, : self.n_vocab].clone()
             if bool((buf.finished != 0).all()):  # one D2H sync per `poll` steps
@@ -527,39 +489,8 @@ class ValleEngine:
             tmp = self._text_prenet(tmp, prenet[1], prenet[0])
         ops.add_pe(tmp, pe, alpha.detach(), x, n, positions=pos, out_rows=rows)
 
-    def _use_views(self, buf: _ArBuffers, greedy: bool) -> bool:
-        return (greedy and self.use_cuda_graph and self.micro_batches > 1 and self.dtype == torch.bfloat16
-                and buf.B >= 32 and buf.B <= 64)
-
-    def _decode_step_views(self, buf: _ArBuffers, head: L.ArHead):
-        """one decode step of every micro-batch, each replayed on its own stream."""
-        key = (head.pe, head.predict_w, head.audio_emb)
-        main = torch.cuda.current_stream()
-        for v in buf.make_views(self.micro_batches):
-            v.stream.wait_stream(main)
-            with torch.cuda.stream(v.stream):
-                if v.graph is None or v.graph_key != key:
-                    self._launch_step(v, head)   # warm-up == this step
-                    g = torch.cuda.CUDAGraph()
-                    n0 = self.lib.vb_launch_count()
-                    with torch.cuda.graph(g, stream=v.stream):
-                        self._launch_step(v, head)
-                    v.graph_kernels = self.lib.vb_launch_count() - n0
-                    self.captured_launches += v.graph_kernels
-                    v.graph, v.graph_key, v.graph_head = g, key, head
-                else:
-                    v.graph.replay()
-                    self.replayed_launches += v.graph_kernels
-
-    def _join_views(self, buf: _ArBuffers):
-        main = torch.cuda.current_stream()
-        for v in buf.views:
-            main.wait_stream(v.stream)
-
     def _decode_step(self, buf: _ArBuffers, head: L.ArHead, greedy: bool, top_k: int, temperature: float,
                      forced_step: Optional[torch.Tensor] = None):
-        if self._use_views(buf, greedy):
-            return self._decode_step_views(buf, head)
         if greedy and self.use_cuda_graph:
             key = (head.pe, head.predict_w, head.audio_emb)
             if buf.graph is not None and buf.graph_key != key:

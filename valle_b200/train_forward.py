@@ -4,8 +4,8 @@ Embeddings + sine PE, the AR stack over padded [text | audio] rows with the merg
 NAR stage with AdaLN, the prediction heads (tensor-core GEMMs in bf16 mode), cross-entropy and top-10 accuracy.
 With gradients enabled (bin/trainer.py:525-531,674: `loss = model(...)`, `scaler.scale(loss).backward()`) every step
 goes through the autograd bridges of valle_b200/autograd.py, whose backward runs the gradient kernels of
-csrc/backward.cu; under torch.no_grad() (validation) the same kernels run without recording.  Dropout is not
-applied in training mode (p treated as 0).
+csrc/backward.cu; under torch.no_grad() (validation) the same kernels run without recording.  In training mode
+(`model.train()`) the reference's Dropout sites are live: stateless hashed masks inside the kernels.
 """
 from __future__ import annotations
 
@@ -98,22 +98,35 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
         eng = model.engine()
         eng._refresh()
 
-    def embed_pe(tokens, table, pos_mod, T, text_prenet=None):
-        """[N, T] ids -> [N, T, d] = prenet(table[ids]) + alpha * pe[:T]."""
+    def embed_pe(tokens, table, pos_mod, T, text_prenet=None, site=None):
+        """[N, T] ids -> [N, T, d] = dropout(prenet(table[ids]) + alpha * pe[:T])."""
         tok = tokens.reshape(-1).contiguous()
         e = AG.EmbedSum.apply(tok, 1, 0, tok.numel(), table)
         if eng is not None and text_prenet is not None:
             # the reference convolves the padded batch: pad-token embeddings inside, zeros beyond the longest text
             e = eng._text_prenet(e, [T] * N, text_prenet)
-        return add_pe(e.view(N, T, table.shape[1]), pos_mod, T)
+        return add_pe(e.view(N, T, table.shape[1]), pos_mod, T, site)
 
-    def add_pe(e, pos_mod, T):
-        return AG.AddPe.apply(e, pos_mod.table(T, dev), pos_mod.alpha)
+    # training mode (model.train(), bin/trainer.py:512): the Dropout modules of the reference are live -- after every
+    # positional encoding (embedding.py:97; p = 0.1, nar_text 0.0) and inside the layers (attention probabilities,
+    # both sub-layer outputs, FFN hidden; transformer.py:315-334, p = 0.1).  One seed per call from the device's
+    # generator, which is the one the reference's dropout kernels consume (torch.manual_seed reproduces a step, the CPU
+    # stream of prefix_len / nar_stage stays aligned with the reference); the masks are the library's stateless hash.
+    drop_seed = int(torch.randint(0, 2 ** 62, (1,), device=dev).item()) if model.training else 0
+    pe_sites = {"ar_text": 1, "ar_audio": 2, "nar_text": 3, "nar_audio": 4}
 
-    def stack(enc, nd, rows, seg1_lens, mode, ada=None, Lp=None):
+    def add_pe(e, pos_mod, T, site=None):
+        out = AG.AddPe.apply(e, pos_mod.table(T, dev), pos_mod.alpha)
+        if model.training and site is not None and pos_mod.dropout.p > 0:
+            out = AG.Dropout.apply(out, pos_mod.dropout.p, drop_seed, 0x10000 + pe_sites[site])
+        return out
+
+    def stack(enc, nd, rows, seg1_lens, mode, ada=None, Lp=None, seed_offset=0):
         cu = (torch.arange(N + 1, dtype=torch.int32, device=dev) * Lp).contiguous()
-        if want_grad:
-            return AG.DecoderStack.apply(rows, ada, nd, (cu, N, Lp, mode, xl32, seg1_lens, Smax), *AG.layer_params(enc))
+        p_layer = float(enc.layers[0].dropout.p) if model.training else 0.0
+        if want_grad or p_layer > 0:
+            return AG.DecoderStack.apply(rows, ada, nd, (cu, N, Lp, mode, xl32, seg1_lens, Smax, p_layer,
+                                                         drop_seed + seed_offset), *AG.layer_params(enc))
         nd.forward(rows, cu, N, Lp, mode, xl32, ada, seg1_lens=seg1_lens, seg1_start=Smax)
         return rows
 
@@ -135,10 +148,10 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
 
     # ---- AR decoder (valle.py:828-881) ----
     if train_stage in (0, 1):
-        xe = embed_pe(text, model.ar_text_embedding.weight, model.ar_text_position, Smax, "ar_text")
+        xe = embed_pe(text, model.ar_text_embedding.weight, model.ar_text_position, Smax, "ar_text", "ar_text")
         Ta = yin.shape[1]                     # Tmax, or Tmax + 1 with the prepended <BOS> (valle.py:820-826,833)
         ar_table = eng.ar_audio_table if eng is not None else model.ar_audio_embedding.weight   # pre-net(embedding)
-        ye = embed_pe(yin.contiguous(), ar_table, model.ar_audio_position, Ta)
+        ye = embed_pe(yin.contiguous(), ar_table, model.ar_audio_position, Ta, None, "ar_audio")
         rows = torch.cat([xe, ye], dim=1).reshape(N * (Smax + Ta), d).contiguous()
         nd = model.ar_decoder.native(dtype)
         yl_ar = (yl32 + (Ta - Tmax)).contiguous()
@@ -159,7 +172,7 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
     if train_stage in (0, 2):
         num_nar_layers = Q - 1
         nar_stage = model.rng.choices([_k for _k in range(1, Q)], weights=[1.0 / num_nar_layers] * num_nar_layers, k=1)[0]
-        xe = embed_pe(text, model.nar_text_embedding.weight, model.nar_text_position, Smax, "nar_text")
+        xe = embed_pe(text, model.nar_text_embedding.weight, model.nar_text_position, Smax, "nar_text", "nar_text")
         emb = [e.weight for e in model.nar_audio_embeddings]
         yq = codes[..., 0].contiguous()
         pm = model.prefix_mode
@@ -204,12 +217,12 @@ def _valle_forward(model, x: torch.Tensor, x_lens: torch.Tensor, y, y_lens, redu
             tg = tg[:, prefix_len:]
         if eng is not None:   # valle.py:918
             y_emb = eng._audio_prenet(y_emb.reshape(N * Ty, -1).contiguous(), "nar_audio").view(N, Ty, -1)
-        y_pos = add_pe(y_emb.contiguous(), model.nar_audio_position, Ty)
+        y_pos = add_pe(y_emb.contiguous(), model.nar_audio_position, Ty, "nar_audio")
         Lp = Smax + Ty
         rows = torch.cat([xe, y_pos], dim=1).reshape(N * Lp, xe.shape[-1]).contiguous()
         nd = model.nar_decoder.native(dtype)
         ada = ada_table(model.nar_decoder, nd, model.nar_stage_embeddings[nar_stage - 1].weight)
-        rows = stack(model.nar_decoder, nd, rows, seg1, L.VB_MASK_PADDED, ada, Lp)
+        rows = stack(model.nar_decoder, nd, rows, seg1, L.VB_MASK_PADDED, ada, Lp, seed_offset=1)
         off = Smax + prefix_len
         if pm == 4:
             off = Smax + prefix_len
