@@ -43,7 +43,8 @@ class TokenEmbedding(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.training and self.dropout.p > 0:
-            raise NotImplementedError("valle_b200: training-mode dropout is not built (inference engine)")
+            raise NotImplementedError("valle_b200: the module-level forward is inference only (training-mode dropout "
+                                      "is applied by VALLE.forward, valle_b200/train_forward.py); call .eval()")
         w = self.word_embeddings.weight
         tok = x.reshape(-1).to(torch.int64).contiguous()
         out = torch.empty((tok.numel(), self.dim_model), dtype=torch.float32, device=w.device)
@@ -80,7 +81,8 @@ class SinePositionalEmbedding(nn.Module):
         if self.x_scale != 1.0:
             raise NotImplementedError("valle_b200: scale=True is not on the VALL-E path")
         if self.training and self.dropout.p > 0:
-            raise NotImplementedError("valle_b200: training-mode dropout is not built (inference engine)")
+            raise NotImplementedError("valle_b200: the module-level forward is inference only (training-mode dropout "
+                                      "is applied by VALLE.forward, valle_b200/train_forward.py); call .eval()")
         assert x.dim() == 3 and x.dtype == torch.float32
         B, T, d = x.shape
         pe = self.table(T, x.device)
