@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 3
+#define VB_ABI_VERSION 4
 
 enum vb_status { VB_OK = 0, VB_ERR_ARG = 1, VB_ERR_CUDA = 2, VB_ERR_UNSUPPORTED = 3 };
 /* storage type of the big matrices / activations.  Accumulation is always fp32. */
@@ -257,6 +257,27 @@ int vb_attention_backward(const void *qkv, const void *out, const void *dout, in
  * a1  AR sampling loop of VALLE.inference (valle.py:1012-1057) with a growing KV cache,
  *     batched over B independent utterances.  All loop state lives on the device.
  * ---------------------------------------------------------------------------------------- */
+/* A LayerNorm folded into the projection that consumes it (bf16 decode chain, valle/modules/transformer.py:296-302:
+ * `x + sa(norm1(x))`, `x + ff(norm2(x))`, valle/models/valle.py:1039 `ar_predict_layer(norm(x))`):
+ *   LayerNorm(x) W^T + b = rstd (x wf^T - mean c) + dvec,  wf[n,k] = W[n,k] gamma[k],  c[n] = sum_k wf[n,k],
+ *   dvec[n] = b[n] + sum_k beta[k] W[n,k]
+ * so the decode step multiplies the RAW fp32 residual rows (rounded to bf16 on the fly) by wf and the consumer of the
+ * product applies the row moments: the residual + LayerNorm launches between the projections disappear.
+ * Built by vb_ln_fold_build; all-NULL = not folded. */
+typedef struct vb_ln_fold {
+  const void *wf;     /* bf16 [N, K] */
+  const float *c;     /* fp32 [N] */
+  const float *dvec;  /* fp32 [N] */
+} vb_ln_fold;
+
+/* W: bf16 [N, K]; gamma, beta: fp32 [K] LayerNorm affine; bias: fp32 [N] or NULL; outputs as in vb_ln_fold */
+int vb_ln_fold_build(const void *W, int N, int K, const float *gamma, const float *beta, const float *bias,
+                     void *wf, float *c, float *dvec, vb_stream_t stream);
+
+/* hands the decoder the folded in_proj (norm1) and linear1 (norm2) of every layer (host arrays [n_layer], copied);
+ * NULL, NULL switches the folded decode chain off again.  bf16 decoders only; used by vb_ar_decode_step. */
+int vb_decoder_set_decode_fold(vb_decoder_t dec, const vb_ln_fold *qkv, const vb_ln_fold *ffn1);
+
 typedef struct vb_ar_state {
   int32_t B;
   int32_t tok_stride;         /* row stride of `tokens` */
@@ -283,6 +304,7 @@ typedef struct vb_ar_head {
   const float *pe;            /* fp32 [pe_rows, d] sine table */
   int32_t pe_rows;
   int32_t greedy;             /* 1: argmax + stop rule + append on device; 0: logits only */
+  vb_ln_fold fold;            /* final LayerNorm folded into predict_w (all-NULL: separate LayerNorm launch) */
 } vb_ar_head;
 
 /* bytes of scratch for vb_ar_head_step / vb_ar_decode_step.  The buffer must not be shared between

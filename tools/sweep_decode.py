@@ -25,13 +25,13 @@ texts, prompts = bench.make_batch(B, 0, dev)
 mnt = None if frames >= bench.FRAMES else frames
 touched = {}
 res = []
-for rep in range(2):
+for rep in range(int(os.environ.get("SWEEP_REPS", "2"))):
     for c in cfgs:
         for k in touched:                      # back to defaults
             lib.vb_tune_set(k.encode(), touched[k])
         kv = dict(x.split("=") for x in c.split(",") if x)
         for k, v in kv.items():
-            touched.setdefault(k, {"VB_KV_PREFETCH_PCT": 40}.get(k, 0))
+            touched.setdefault(k, {"VB_KV_PREFETCH_PCT": 40, "VB_DECODE_FOLD": 1}.get(k, 0))
             lib.vb_tune_set(k.encode(), int(v))
         eng._bufs.clear()
         eng.generate(texts, prompts, top_k=1, max_new_tokens=min(40, frames), return_device=True)   # capture

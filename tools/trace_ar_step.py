@@ -68,7 +68,8 @@ def main():
         d = [s[p + 1][0] - s[p][0] for s in steps_ev]
         pos_stats.append((NAMES.get(steps_ev[0][p][1], "?"), sum(d) / len(d) / 1000.0))
     total = sum(v for _, v in pos_stats)
-    per_layer = (L0 - 3) // 12 if (L0 - 3) % 12 == 0 else None
+    # 8 kernels per layer + LN / head / sampler, or (LayerNorm-folded chain) 6 per layer + head / sampler
+    per_layer = (L0 - 3) // 12 if (L0 - 3) % 12 == 0 else ((L0 - 2) // 12 if (L0 - 2) % 12 == 0 else None)
     print(f"sum of stage times {total:.1f} us (block-0 stamps, last {len(steps_ev)} steps)")
     agg = {}
     for nm, v in pos_stats:

@@ -12,7 +12,7 @@ from typing import Optional
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvalle_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 VB_F32, VB_BF16 = 0, 1
 VB_EPI_NONE, VB_EPI_RELU, VB_EPI_RESIDUAL = 0, 1, 2
 VB_MASK_FULL, VB_MASK_VALLE_AR, VB_MASK_PADDED_AR, VB_MASK_PADDED, VB_MASK_DENSE = 0, 1, 2, 3, 4
@@ -47,11 +47,16 @@ class ArState(C.Structure):
                 ("cache_cap", C.c_int32), ("_unused", C.c_int32)]
 
 
+class LnFold(C.Structure):
+    """vb_ln_fold: a LayerNorm folded into the projection that consumes it (bf16 decode chain)"""
+    _fields_ = [("wf", vp), ("c", vp), ("dvec", vp)]
+
+
 class ArHead(C.Structure):
     """vb_ar_head: ar_predict_layer + the embedding / position tables the sampler needs for the next row"""
     _fields_ = [("predict_w", vp), ("n_vocab", C.c_int32), ("eos_id", C.c_int32),
                 ("audio_emb", vp), ("alpha", vp), ("pe", vp),
-                ("pe_rows", C.c_int32), ("greedy", C.c_int32)]
+                ("pe_rows", C.c_int32), ("greedy", C.c_int32), ("fold", LnFold)]
 
 
 class LayerGrads(C.Structure):
@@ -116,6 +121,8 @@ PROTOTYPES = {
     "vb_attention_backward_workspace": (C.c_size_t, [C.c_int64, C.c_int]),
     "vb_attention_backward": (C.c_int, [vp, vp, vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_int,
                                         C.c_int, C.c_int, vp, vp, C.c_size_t, vp]),
+    "vb_ln_fold_build": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+    "vb_decoder_set_decode_fold": (C.c_int, [vp, C.POINTER(LnFold), C.POINTER(LnFold)]),
     "vb_ar_step_workspace": (C.c_size_t, [C.POINTER(DecoderDesc), C.c_int, C.c_int]),
     "vb_ar_head_step": (C.c_int, [vp, C.POINTER(ArHead), vp, C.POINTER(ArState), vp, C.c_size_t, vp]),
     "vb_ar_decode_step": (C.c_int, [vp, C.POINTER(ArHead), C.POINTER(ArState), vp, C.c_size_t, vp]),

@@ -55,6 +55,7 @@ using namespace vb;
 struct vb_decoder {
   vb_decoder_desc desc;
   vb_layer_params *layers;  // owned host copy
+  vb_ln_fold *fold_qkv = nullptr, *fold_ffn1 = nullptr;  // owned host copies [n_layer] or NULL (vb_decoder_set_decode_fold)
 };
 
 VB_API int vb_abi_version(void) { return VB_ABI_VERSION; }
@@ -133,7 +134,41 @@ VB_API int vb_decoder_create(const vb_decoder_desc *desc, vb_decoder_t *out) {
 VB_API void vb_decoder_destroy(vb_decoder_t dec) {
   if (!dec) return;
   delete[] dec->layers;
+  delete[] dec->fold_qkv;
+  delete[] dec->fold_ffn1;
   delete dec;
+}
+
+VB_API int vb_ln_fold_build(const void *W, int N, int K, const float *gamma, const float *beta, const float *bias,
+                            void *wf, float *c, float *dvec, vb_stream_t stream) {
+  VB_CHECK_ARG(W && gamma && beta && wf && c && dvec && N > 0 && K > 0, "vb_ln_fold_build: null argument / bad shape");
+  return launch_ln_fold((const bf16 *)W, N, K, gamma, beta, bias, (bf16 *)wf, c, dvec, (cudaStream_t)stream);
+}
+
+VB_API int vb_decoder_set_decode_fold(vb_decoder_t dec, const vb_ln_fold *qkv, const vb_ln_fold *ffn1) {
+  VB_CHECK_ARG(dec, "vb_decoder_set_decode_fold: null decoder");
+  delete[] dec->fold_qkv;
+  delete[] dec->fold_ffn1;
+  dec->fold_qkv = dec->fold_ffn1 = nullptr;
+  if (!qkv && !ffn1) return VB_OK;
+  VB_CHECK_ARG(qkv && ffn1, "vb_decoder_set_decode_fold: both arrays or neither");
+  VB_CHECK_ARG(dec->desc.wdtype == VB_BF16, "vb_decoder_set_decode_fold: bf16 decoders only");
+  const int n = dec->desc.n_layer;
+  for (int l = 0; l < n; ++l)
+    VB_CHECK_ARG(qkv[l].wf && qkv[l].c && qkv[l].dvec && ffn1[l].wf && ffn1[l].c && ffn1[l].dvec,
+                 "vb_decoder_set_decode_fold: layer %d has a null pointer", l);
+  dec->fold_qkv = new (std::nothrow) vb_ln_fold[n];
+  dec->fold_ffn1 = new (std::nothrow) vb_ln_fold[n];
+  if (!dec->fold_qkv || !dec->fold_ffn1) {
+    delete[] dec->fold_qkv;
+    delete[] dec->fold_ffn1;
+    dec->fold_qkv = dec->fold_ffn1 = nullptr;
+    set_error("vb_decoder_set_decode_fold: out of host memory");
+    return VB_ERR_ARG;
+  }
+  memcpy(dec->fold_qkv, qkv, sizeof(vb_ln_fold) * n);
+  memcpy(dec->fold_ffn1, ffn1, sizeof(vb_ln_fold) * n);
+  return VB_OK;
 }
 
 static size_t elem_size(int dtype) { return dtype == VB_BF16 ? 2 : 4; }
@@ -377,6 +412,7 @@ struct StepWs {
   void *attn_ws;
   bf16 *xn16, *att16, *hb16;
   void *gemm_ws;
+  float *stats;  // moments of the folded-LayerNorm projections: [kMaxForcedSplits][64][2]
   size_t gemm_ws_bytes;
   size_t total;
 };
@@ -398,6 +434,7 @@ StepWs carve_step_ws(const vb_decoder_desc &D, int B, int cache_cap, void *base)
   w.hb16 = (bf16 *)take((size_t)64 * dff * 2);
   w.gemm_ws_bytes = gemm_decode_workspace((int)d, (int)dff);
   w.gemm_ws = take(w.gemm_ws_bytes);
+  w.stats = (float *)take((size_t)kMaxForcedSplits * 64 * 2 * sizeof(float));
   w.total = (size_t)(p - (char *)base) + 256;
   return w;
 }
@@ -426,6 +463,15 @@ int tc_head(vb_decoder *dec, const vb_ar_head *head, float *x, vb_ar_state *st, 
   const int d = D.d_model, B = st->B;
   const int ldl = (head->n_vocab + 3) & ~3;
   const bool pdl = use_pdl();
+  if (head->fold.wf && pend.part == nullptr && tune("VB_DECODE_FOLD", 1) != 0) {
+    // final LayerNorm folded into ar_predict_layer: the projection reads the fp32 rows, the sampler applies the moments
+    int sp = 1, ldp = 0;
+    VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)head->fold.wf, head->n_vocab, d, 0, (float *)w.gemm_ws,
+                                w.gemm_ws_bytes, w.stats, &sp, &ldp, nullptr, pdl, s));
+    const LnFoldStats fs{w.stats, head->fold.c, sp, d, 1e-5f};
+    return launch_ar_sample(st->logits, ldl, (const float *)w.gemm_ws, sp, ldp, head, st, d, nullptr,
+                            head->greedy ? 0 : 1, pdl, s, &fs);
+  }
   VB_TRY(launch_ln_reduce(x, d, B, d, pend.part, pend.splits, pend.ldp, pend.bias, D.final_norm_w, D.final_norm_b,
                           1e-5f, w.xn16, pdl, s));
   int sp = 1, ldp = 0;
@@ -512,6 +558,41 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
       pf.lo_pct = pf_pct * quarter / 4; pf.hi_pct = pf_pct * (quarter + 1) / 4;
       return pf;
     };
+    const bool fold = dec->fold_qkv && dec->fold_ffn1 && head->fold.wf && tune("VB_DECODE_FOLD", 1) != 0;
+    if (fold) {
+      // Folded chain, 6 launches per layer: the residual stream x is assembled in place by the split-K projections that
+      // produce it (red.global.add of every split's tile), the projections that consume it read the fp32 rows and carry
+      // the LayerNorm in their weights (vb_ln_fold), the rows' moments travel with the partial sums:
+      //   QKV'(x) -> attention (+ moments, KV append) -> out-proj (+= x) -> FFN1'(x) -> ReLU reduce (+ moments) -> FFN2 (+= x)
+      const int qkv_f = qkv_env > 0 ? qkv_env : std::max(1, std::min(5, d / 128));
+      const int ffn1_f = ffn1_env > 0 ? ffn1_env : std::max(1, std::min(4, d / 128));
+      const int out_f = out_splits > 0 ? out_splits : 8;
+      for (int l = 0; l < D.n_layer; ++l) {
+        const vb_layer_params &L = dec->layers[l];
+        const vb_ln_fold &Fq = dec->fold_qkv[l], &Ff = dec->fold_ffn1[l];
+        const KvPrefetch pf_qkv = kv_slice(l, 3), pf_out = kv_slice(l + 1, 0), pf_f1 = kv_slice(l + 1, 1),
+                         pf_f2 = kv_slice(l + 1, 2);
+        void *kc = (char *)st->kcache + (size_t)l * st->cache_layer_stride * ts;
+        void *vc = (char *)st->vcache + (size_t)l * st->cache_layer_stride * ts;
+        int s1 = 1, ldp1 = 0;
+        VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)Fq.wf, 3 * d, d, qkv_f, P, w.gemm_ws_bytes, w.stats, &s1, &ldp1,
+                                    &pf_qkv, pdl, s));
+        const LnFoldStats fq{w.stats, Fq.c, s1, d, 1e-5f};
+        VB_TRY(launch_attn_decode(w.q, P, s1, ldp1, Fq.dvec, B, D.n_head, hd, kc, vc, dt, st->cache_seq_stride,
+                                  st->cache_cap, st->text_len, st->prompt_len, st->n_gen, st->finished, w.att, w.att16,
+                                  w.attn_ws, pdl, s, &fq));
+        VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)L.out_proj_w, d, d, out_f, L.out_proj_b, DG_RESIDUAL, x,
+                                  nullptr, d, nullptr, nullptr, 0, nullptr, nullptr, &pf_out, pdl, s, true));
+        int sf = 1, ldpf = 0;
+        VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)Ff.wf, dff, d, ffn1_f, P, w.gemm_ws_bytes, w.stats, &sf, &ldpf,
+                                    &pf_f1, pdl, s));
+        const LnFoldStats ff{w.stats, Ff.c, sf, d, 1e-5f};
+        VB_TRY(launch_relu_reduce(P, sf, ldpf, Ff.dvec, B, dff, w.hb16, dff, pdl, s, &ff));
+        VB_TRY(launch_gemm_decode(w.hb16, B, dff, (const bf16 *)L.lin2_w, d, dff, ffn2_splits, L.lin2_b, DG_RESIDUAL, x,
+                                  nullptr, d, nullptr, nullptr, 0, nullptr, nullptr, &pf_f2, pdl, s, true));
+      }
+      return tc_head(dec, head, x, st, w, Pending{}, s);
+    }
     for (int l = 0; l < D.n_layer; ++l) {
       const vb_layer_params &L = dec->layers[l];
       const KvPrefetch pf_qkv = kv_slice(l, 3), pf_out = kv_slice(l + 1, 0), pf_f1 = kv_slice(l + 1, 1),

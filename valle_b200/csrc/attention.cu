@@ -251,8 +251,9 @@ template <> __device__ __forceinline__ void KvRow8<bf16>::load(const bf16 *p, fl
 // cache (split 0) and serves the new key/value from shared memory.
 struct QkvPartials {
   const float *part;  // [splits][64][ldp] or nullptr
-  const float *bias;  // [3d]
+  const float *bias;  // [3d] (with a folded LayerNorm: bias + beta W^T)
   int splits, ldp;
+  LnFoldStats fold;   // fold.stats != NULL: the partials are x (gamma o W)^T of the raw rows (gemm_decode_x_kernel)
 };
 
 // A finished utterance (stop rule fired, vb_ar_state.finished != 0) takes no further part in the step: its KV
@@ -320,6 +321,11 @@ attn_decode_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *_
         float acc = __ldcg(p);
 #pragma unroll 6
         for (int s = 1; s < qp.splits; ++s) acc += __ldcg(p + (int64_t)s * 64 * qp.ldp);
+        if (qp.fold.stats) {
+          float mean, rstd;
+          ln_fold_moments(qp.fold, b, mean, rstd);
+          acc = rstd * (acc - mean * qp.fold.c[col]);
+        }
         a[j] = acc + qp.bias[col];
       }
       qs[tid] = a[0] * 0.125f;
@@ -475,10 +481,13 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
   // row was written to the cache by the kernel this launch depends on and nothing may be read ahead of the wait)
   const int n_gen_early = has_new ? n_gen[b] : -1;
   if (has_new) setup(n_gen_early);
-  float qbias[3] = {0.f, 0.f, 0.f};
+  float qbias[3] = {0.f, 0.f, 0.f}, qc[3] = {0.f, 0.f, 0.f};
   if (tid < HD && has_new) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) qbias[j] = qp.bias[j * d + h * HD + tid];
+    for (int j = 0; j < 3; ++j) {
+      qbias[j] = qp.bias[j * d + h * HD + tid];
+      if (qp.fold.stats) qc[j] = qp.fold.c[j * d + h * HD + tid];
+    }
   }
   pdl_wait();
   vb_trace(TR_ATTN * 2);
@@ -489,13 +498,25 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
   if (tid < HD) {
     if (has_new) {
       float a[3];
+      // all partial sums of the three columns (and the rows' moments) requested in one round trip
+      constexpr int kU = 8;
+      float pv[3][kU];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const int col = j * d + h * HD + tid;
-        const float *p = qp.part + (int64_t)b * qp.ldp + col;
-        float acc = p[0];
-        for (int s = 1; s < qp.splits; ++s) acc += p[(int64_t)s * 64 * qp.ldp];
-        a[j] = acc + qbias[j];
+        const float *p = qp.part + (int64_t)b * qp.ldp + j * d + h * HD + tid;
+#pragma unroll
+        for (int s = 0; s < kU; ++s) pv[j][s] = s < qp.splits ? __ldcg(p + (int64_t)s * 64 * qp.ldp) : 0.f;
+      }
+      float mean = 0.f, rstd = 1.f;
+      if (qp.fold.stats) ln_fold_moments(qp.fold, b, mean, rstd);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float acc = pv[j][0];
+#pragma unroll
+        for (int s = 1; s < kU; ++s) acc += pv[j][s];   // fixed order 0..S-1 (the tail adds exact zeros)
+        const float *p = qp.part + (int64_t)b * qp.ldp + j * d + h * HD + tid;
+        for (int s = kU; s < qp.splits; ++s) acc += __ldcg(p + (int64_t)s * 64 * qp.ldp);
+        a[j] = rstd * (acc - mean * qc[j]) + qbias[j];
       }
       qs[tid] = a[0] * 0.125f;
       const T k16 = from_f32<T>(a[1]), v16 = from_f32<T>(a[2]);
@@ -669,13 +690,14 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
                        int B, int n_head, int head_dim, void *kcache, void *vcache, int dtype,
                        int64_t cache_seq_stride, int cache_cap, const int32_t *text_len, const int32_t *prompt_len,
                        const int32_t *n_gen, const int32_t *finished, float *out, void *out16, void *workspace,
-                       bool pdl, cudaStream_t s) {
+                       bool pdl, cudaStream_t s, const LnFoldStats *fold) {
   VB_CHECK_ARG(head_dim == HD, "attn_decode: head_dim=%d, only 64 is built", head_dim);
   const int ns = decode_nsplit(B, n_head, cache_cap);
   VB_CHECK_ARG((cache_cap + ns - 1) / ns + 16 <= kDecMaxChunk, "attn_decode: cache_cap %d too large", cache_cap);
   float *part_o = (float *)workspace;
   float *part_ml = part_o + (size_t)B * n_head * ns * HD;
-  QkvPartials qp{qkv_part, qkv_bias, qkv_splits, qkv_ldp};
+  QkvPartials qp{qkv_part, qkv_bias, qkv_splits, qkv_ldp, LnFoldStats{}};
+  if (fold) qp.fold = *fold;
   dim3 grid(n_head, B, ns);
   if (dtype == VB_F32 || getenv("VB_ATTN_DECODE_1PASS") != nullptr) {  // fp32 parity path / single-pass variant
     if (dtype == VB_F32)

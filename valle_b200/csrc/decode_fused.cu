@@ -104,20 +104,28 @@ ln_reduce_kernel(float *__restrict__ x, int64_t ldx, int B, int d, const float *
 // (valle/modules/transformer.py:332-334: linear1 -> ReLU), input rows of the linear2 projection.
 __global__ void __launch_bounds__(256)
 relu_reduce_kernel(const float *__restrict__ partials, int splits, int ldp, const float *__restrict__ bias, int N,
-                   bf16 *__restrict__ out16, int64_t ldo) {
+                   bf16 *__restrict__ out16, int64_t ldo, LnFoldStats fold) {
   pdl_launch_dependents();
   const int b = blockIdx.y;
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   const float4 bb = c < N ? *reinterpret_cast<const float4 *>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);  // ahead of the wait
+  float4 cc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (fold.stats && c < N) cc = *reinterpret_cast<const float4 *>(fold.c + c);
   pdl_wait();
   vb_trace(TR_RELU * 2);
   if (c >= N) return;
   const float *p = partials + (int64_t)b * ldp + c;
+  float mean = 0.f, rstd = 1.f;
+  if (fold.stats) ln_fold_moments(fold, b, mean, rstd);   // requested ahead of the partial sums: one round trip for both
   float4 a = __ldcg(reinterpret_cast<const float4 *>(p));
 #pragma unroll 4
   for (int s = 1; s < splits; ++s) {
     const float4 t = __ldcg(reinterpret_cast<const float4 *>(p + (int64_t)s * 64 * ldp));
     a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+  }
+  if (fold.stats) {  // LayerNorm folded into linear1: relu(rstd (x W'^T - mean c) + bias')
+    a.x = rstd * (a.x - mean * cc.x); a.y = rstd * (a.y - mean * cc.y);
+    a.z = rstd * (a.z - mean * cc.z); a.w = rstd * (a.w - mean * cc.w);
   }
   __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(a.x + bb.x, 0.f), fmaxf(a.y + bb.y, 0.f));
   __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaxf(a.z + bb.z, 0.f), fmaxf(a.w + bb.w, 0.f));
@@ -128,10 +136,12 @@ relu_reduce_kernel(const float *__restrict__ partials, int splits, int ldp, cons
 }
 
 int launch_relu_reduce(const float *partials, int splits, int ldp, const float *bias, int B, int N, bf16 *out16,
-                       int64_t ldo, bool pdl, cudaStream_t s) {
+                       int64_t ldo, bool pdl, cudaStream_t s, const LnFoldStats *fold) {
   VB_CHECK_ARG(N % 4 == 0 && ldo % 4 == 0, "relu_reduce: N %% 4 != 0");
+  LnFoldStats f{};
+  if (fold) f = *fold;
   VB_CUDA(launch_kernel(relu_reduce_kernel, dim3((N / 4 + 255) / 256, B), dim3(256), 0, s, pdl, partials, splits, ldp,
-                        bias, N, out16, ldo));
+                        bias, N, out16, ldo, f));
   count_launch();
   return VB_OK;
 }

@@ -40,6 +40,7 @@ constexpr int kTmemCols = 64;
 
 struct Epi {
   int mode;  // DG_* below
+  int red;   // DG_RESIDUAL with split-K: every split adds its tile into out_f32 with red.global.add (no partials)
   int N, B;  // valid output features / rows
   const float *bias;
   float *out_f32;      // [B, ld_out] (RESIDUAL: in/out; F32: out; QKV: q)
@@ -77,7 +78,8 @@ __device__ __forceinline__ void apply_epi(const Epi &e, int n, int b, float v) {
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
-                   int num_kb, float *__restrict__ partials, int ldp, Epi epi, KvPrefetch pf) {
+                   const __grid_constant__ CUtensorMap tmap_red, int num_kb, float *__restrict__ partials, int ldp,
+                   Epi epi, KvPrefetch pf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kStages * kStageBytes);
@@ -95,6 +97,7 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_w);
     prefetch_tmap(&tmap_x);
+    if (epi.red) prefetch_tmap(&tmap_red);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -194,12 +197,219 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       __syncwarp();
       if (n < epi.N)
         for (int b = 0; b < epi.B; ++b) apply_epi(epi, n, b, sv[b * TM + nl]);
+    } else if (epi.red) {
+      // residual stream assembled in place: x[0:B, tile] += this split's tile (+ bias once, from split 0).  The tile
+      // is staged row-major in the (now idle) pipeline shared memory and handed to the TMA engine as ONE bulk tensor
+      // reduction (rows past B are clipped by the tensor map); per-lane red.global.add measured 2 us slower per launch.
+      float *sv = reinterpret_cast<float *>(tiles);  // [TN][TM]
+      const float bias = (split == 0 && epi.bias && n < epi.N) ? epi.bias[n] : 0.f;
+#pragma unroll
+      for (int b = 0; b < TN; ++b) sv[b * TM + nl] = v[b] + bias;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (q == 0 && lane == 0) {
+        tma_reduce_add_2d(&tmap_red, sv, tile * TM, 0);
+        tma_store_commit();
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // performed before the grid may count as complete
+      }
     } else {
       // partials[split][b][n]: for a fixed row b consecutive lanes write consecutive features
       float *mine = partials + (int64_t)split * TN * ldp + n;
 #pragma unroll
       for (int b = 0; b < TN; ++b) mine[(int64_t)b * ldp] = v[b];
     }
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+  vb_trace(TR_GEMM * 2 + 1);
+}
+
+// ---- the same projection fed from the fp32 residual stream, LayerNorm folded into the weights ----------------
+// LayerNorm(x) W^T = rstd (x (gamma o W)^T - mean c) + (beta W^T),  c[n] = sum_k gamma[k] W[n,k]: the tensor cores
+// multiply the RAW rows by the pre-scaled weights, every CTA turns the fp32 rows of its k-range into the bf16
+// 128B-swizzled operand tile itself (TMA brings the fp32 box, 8 warps convert it), and the moments of the rows
+// (sum x, sum x^2 over the k-range) ride along as two more partial sums per split.  The consumer of the partials
+// (attention prologue / ReLU reduce / sampler) applies rstd, mean, c and the folded bias -- the separate
+// residual + LayerNorm launch between two projections (transformer.py:296-302,57-74) disappears from the chain.
+constexpr int kStagesX = 4;   // the chain's split counts keep a CTA at <= 4 k-blocks: the ring never wraps
+constexpr int kXfBytes = TN * BK * 4;  // 16 KB fp32 box
+constexpr int kStageBytesX = kWBytes + kXBytes + kXfBytes;  // 40 KB
+constexpr int kSmemBytesX = kStagesX * kStageBytesX + 1024 + 512;
+constexpr int kThreadsX = 448;  // warp 0 TMA, 1 MMA, 2..9 converters (4..7 also the epilogue), 10..13 KV prefetch
+
+// (register cap of two CTAs per SM: 72 registers, no spills -- with the 4-stage ring that leaves room for three CTAs of
+//  the attention launch that follows to become resident, and fetch their first K rows, while this kernel still runs)
+__global__ void __launch_bounds__(kThreadsX, 2)
+gemm_decode_x_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_xf,
+                     int num_kb, float *__restrict__ partials, int ldp, float *__restrict__ stats, KvPrefetch pf) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kStagesX * kStageBytesX);
+  uint64_t *wfull = bars, *xfull = bars + kStagesX, *bfull = bars + 2 * kStagesX, *empty_bar = bars + 3 * kStagesX,
+           *tmem_full = bars + 4 * kStagesX;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, split = blockIdx.y, splits = gridDim.y;
+  const int base = num_kb / splits, rem = num_kb % splits;
+  const int kb0 = split * base + min(split, rem);
+  const int nkb = base + (split < rem ? 1 : 0);
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_xf);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStagesX; ++i) {
+      mbar_init(&wfull[i], 1);
+      mbar_init(&xfull[i], 1);
+      mbar_init(&bfull[i], 8);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int pre = min(nkb, kStagesX);
+      for (int i = 0; i < pre; ++i) {  // weights: independent of the previous kernel
+        mbar_expect_tx(&wfull[i], kWBytes);
+        tma_load_2d(&tmap_w, &wfull[i], tiles + i * kStageBytesX, (kb0 + i) * BK, tile * TM);
+      }
+      pdl_wait();
+      vb_trace(TR_GEMM * 2);
+      for (int i = 0; i < pre; ++i) {
+        mbar_expect_tx(&xfull[i], kXfBytes);
+        tma_load_2d(&tmap_xf, &xfull[i], tiles + i * kStageBytesX + kWBytes + kXBytes, (kb0 + i) * BK, 0);
+      }
+      int stage = 0;
+      uint32_t phase = 1;
+      for (int i = pre; i < nkb; ++i) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t *dst = tiles + stage * kStageBytesX;
+        mbar_expect_tx(&wfull[stage], kWBytes);
+        tma_load_2d(&tmap_w, &wfull[stage], dst, (kb0 + i) * BK, tile * TM);
+        mbar_expect_tx(&xfull[stage], kXfBytes);
+        tma_load_2d(&tmap_xf, &xfull[stage], dst + kWBytes + kXBytes, (kb0 + i) * BK, 0);
+        if (++stage == kStagesX) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TM, TN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(&wfull[stage], phase);
+        mbar_wait(&bfull[stage], phase);
+        tcgen05_fence_after();
+        const uint32_t w_addr = smem_u32(tiles + stage * kStageBytesX);
+        const uint64_t adesc = make_smem_desc(w_addr);
+        const uint64_t bdesc = make_smem_desc(w_addr + kWBytes);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (i | k) != 0);
+        tcgen05_commit(&empty_bar[stage]);
+        if (++stage == kStagesX) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      tcgen05_commit(tmem_full);
+    }
+    __syncwarp();
+  } else if (warp < 10) {
+    // ---- converters: warp cw owns rows cw*8 .. +8 of every k-block; lane = (row parity, float4 of the row) ----
+    const int cw = warp - 2;
+    const int rsub = lane >> 4, f = lane & 15;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    pdl_wait();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < nkb; ++i) {
+      mbar_wait(&xfull[stage], phase);
+      const uint8_t *xf = tiles + stage * kStageBytesX + kWBytes + kXBytes;
+      uint8_t *xb = tiles + stage * kStageBytesX + kWBytes;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int r = cw * 8 + it * 2 + rsub;
+        const float4 v = *reinterpret_cast<const float4 *>(xf + r * (BK * 4) + f * 16);
+        s1[it] += (v.x + v.y) + (v.z + v.w);
+        s2[it] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2[it]))));
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t *>(&p0);
+        pk.y = *reinterpret_cast<uint32_t *>(&p1);
+        // 128B swizzle of a K-major row: 16-byte chunk c of row r lives at chunk c ^ (r & 7)
+        *reinterpret_cast<uint2 *>(xb + r * 128 + ((((f >> 1) ^ (r & 7))) << 4) + (f & 1) * 8) = pk;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bfull[stage]);
+      if (++stage == kStagesX) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (tile == 0 && stats != nullptr) {  // moments of this split's k-range: stats[split][row][2]
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          s1[it] += __shfl_xor_sync(0xffffffffu, s1[it], o);
+          s2[it] += __shfl_xor_sync(0xffffffffu, s2[it], o);
+        }
+        if (f == 0) {
+          const int r = cw * 8 + it * 2 + rsub;
+          *reinterpret_cast<float2 *>(stats + ((int64_t)split * TN + r) * 2) = make_float2(s1[it], s2[it]);
+        }
+      }
+    }
+    if (warp >= 4 && warp < 8) {  // ---- epilogue: fp32 partial tile of this split, 32 rows at a time ----
+      const int q = warp & 3;
+      const int n = tile * TM + q * 32 + lane;
+      float *mine = partials + (int64_t)split * TN * ldp + n;
+      if (nkb > 0) {
+        mbar_wait(tmem_full, 0);
+        tcgen05_fence_after();
+      }
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        if (nkb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 32), r);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mine[(int64_t)(half * 32 + i) * ldp] = __uint_as_float(r[i]);
+      }
+    }
+  } else {
+    // idle warps: pull a slice of an upcoming layer's KV cache into L2 while the weight tiles stream
+    kv_prefetch(pf, (blockIdx.y * gridDim.x + blockIdx.x) * 4 + (warp - 10), gridDim.x * gridDim.y * 4);
+    pdl_wait();
   }
   __syncwarp();
   tcgen05_fence_before();
@@ -232,23 +442,28 @@ static int pick_splits(int tiles, int num_kb) {
 int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, int N, int K, int force_splits,
                        const float *bias, int mode, float *out_f32, bf16 *out_bf16, int64_t ld_out,
                        const QkvScatter *qkv, float *partials, size_t partial_bytes, int *out_splits, int *out_ldp,
-                       const KvPrefetch *pf, bool pdl, cudaStream_t s) {
+                       const KvPrefetch *pf, bool pdl, cudaStream_t s, bool red_add) {
   VB_CHECK_ARG(B >= 1 && B <= dg::TN, "gemm_decode: B=%d not in [1,64]", B);
+  VB_CHECK_ARG(!red_add || mode == DG_RESIDUAL, "gemm_decode: red_add needs the residual epilogue");
   VB_CHECK_ARG(K % tc::BK == 0 && ld_act % 8 == 0, "gemm_decode: K %% 64 != 0 or unaligned activations");
   const int tiles = (N + dg::TM - 1) / dg::TM;
   const int num_kb = K / tc::BK;
   int splits = force_splits > 0 ? std::min(force_splits, std::min(kMaxForcedSplits, num_kb)) : pick_splits(tiles, num_kb);
   const int ldp = tiles * dg::TM;
-  if (splits > 1)
+  if (splits > 1 && !red_add)
     VB_CHECK_ARG(partials && partial_bytes >= (size_t)splits * dg::TN * ldp * sizeof(float),
                  "gemm_decode: partial buffer too small");
-  if (out_splits) *out_splits = splits;
+  if (out_splits) *out_splits = red_add ? 1 : splits;  // nothing left for a consumer to add up
   if (out_ldp) *out_ldp = ldp;
-  CUtensorMap tw, tx;
+  CUtensorMap tw, tx, tr;
   VB_TRY(tc::make_tmap(&tw, W, N, K, K, dg::TM));
   VB_TRY(tc::make_tmap(&tx, act, B, K, ld_act, dg::TN));
+  if (red_add && splits > 1)
+    VB_TRY(tc::make_tmap_f32_dense(&tr, out_f32, B, N, ld_out, dg::TN, dg::TM));
+  else
+    tr = tw;  // unused
   dg::Epi e{};
-  e.mode = mode; e.N = N; e.B = B; e.bias = bias;
+  e.mode = mode; e.N = N; e.B = B; e.bias = bias; e.red = (red_add && splits > 1) ? 1 : 0;
   e.out_f32 = out_f32; e.out_bf16 = out_bf16; e.ld_out = ld_out;
   if (mode == DG_QKV && splits == 1) {
     VB_CHECK_ARG(qkv != nullptr, "gemm_decode: qkv scatter parameters missing");
@@ -266,7 +481,68 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
   KvPrefetch pf0{};
   if (pf) pf0 = *pf;
   VB_CUDA(launch_kernel(dg::gemm_decode_kernel, dim3(tiles, splits), dim3(dg::kThreads), dg::kSmemBytes, s, pdl, tw,
-                        tx, num_kb, partials, ldp, e, pf0));
+                        tx, tr, num_kb, partials, ldp, e, pf0));
+  count_launch();
+  return VB_OK;
+}
+
+// projection of the fp32 rows x[B, K] by LayerNorm-folded weights: fp32 partial tiles + the rows' moments per split
+int launch_gemm_decode_x(const float *x, int B, int64_t ldx, const bf16 *Wf, int N, int K, int force_splits,
+                         float *partials, size_t partial_bytes, float *stats, int *out_splits, int *out_ldp,
+                         const KvPrefetch *pf, bool pdl, cudaStream_t s) {
+  VB_CHECK_ARG(B >= 1 && B <= dg::TN, "gemm_decode_x: B=%d not in [1,64]", B);
+  VB_CHECK_ARG(K % tc::BK == 0 && ldx % 4 == 0, "gemm_decode_x: K %% 64 != 0 or unaligned rows");
+  const int tiles = (N + dg::TM - 1) / dg::TM;
+  const int num_kb = K / tc::BK;
+  const int splits = force_splits > 0 ? std::min(force_splits, std::min(kMaxForcedSplits, num_kb))
+                                      : pick_splits(tiles, num_kb);
+  const int ldp = tiles * dg::TM;
+  VB_CHECK_ARG(partials && stats && partial_bytes >= (size_t)splits * dg::TN * ldp * sizeof(float),
+               "gemm_decode_x: partial buffer too small");
+  if (out_splits) *out_splits = splits;
+  if (out_ldp) *out_ldp = ldp;
+  CUtensorMap tw, tx;
+  VB_TRY(tc::make_tmap(&tw, Wf, N, K, K, dg::TM));
+  VB_TRY(tc::make_tmap_f32_dense(&tx, x, B, K, ldx, dg::TN, tc::BK));
+  static PerDeviceOnce once;
+  if (once.first())
+    VB_CUDA(cudaFuncSetAttribute(dg::gemm_decode_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 dg::kSmemBytesX));
+  KvPrefetch pf0{};
+  if (pf) pf0 = *pf;
+  VB_CUDA(launch_kernel(dg::gemm_decode_x_kernel, dim3(tiles, splits), dim3(dg::kThreadsX), dg::kSmemBytesX, s, pdl,
+                        tw, tx, num_kb, partials, ldp, stats, pf0));
+  count_launch();
+  return VB_OK;
+}
+
+// ---- LayerNorm folding (host API vb_ln_fold_build): wf[n,k] = bf16(W[n,k] gamma[k]), c[n] = sum_k wf[n,k],
+//      dvec[n] = bias[n] + sum_k beta[k] W[n,k]; one warp per output feature --------------------------------------
+__global__ void __launch_bounds__(256)
+ln_fold_kernel(const bf16 *__restrict__ W, int N, int K, const float *__restrict__ gamma,
+               const float *__restrict__ beta, const float *__restrict__ bias, bf16 *__restrict__ wf,
+               float *__restrict__ c, float *__restrict__ dvec) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, ds = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = __bfloat162float(W[(int64_t)n * K + k]);
+    const bf16 f = __float2bfloat16_rn(w * gamma[k]);
+    wf[(int64_t)n * K + k] = f;
+    cs += __bfloat162float(f);
+    ds = fmaf(beta[k], w, ds);
+  }
+  cs = warp_sum(cs);
+  ds = warp_sum(ds);
+  if (lane == 0) {
+    c[n] = cs;
+    dvec[n] = ds + (bias ? bias[n] : 0.f);
+  }
+}
+int launch_ln_fold(const bf16 *W, int N, int K, const float *gamma, const float *beta, const float *bias, bf16 *wf,
+                   float *c, float *dvec, cudaStream_t s) {
+  VB_CUDA(launch_kernel(ln_fold_kernel, dim3((N + 7) / 8), dim3(256), 0, s, false, W, N, K, gamma, beta, bias, wf, c,
+                        dvec));
   count_launch();
   return VB_OK;
 }

@@ -136,7 +136,36 @@ size_t gemm_decode_workspace(int d_model, int d_ff);
 int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, int N, int K, int force_splits,
                        const float *bias, int mode, float *out_f32, bf16 *out_bf16, int64_t ld_out,
                        const QkvScatter *qkv, float *partials, size_t partial_bytes, int *out_splits, int *out_ldp,
-                       const KvPrefetch *pf, bool pdl, cudaStream_t s);
+                       const KvPrefetch *pf, bool pdl, cudaStream_t s, bool red_add = false);
+// LayerNorm folded into the projection (decode chain without the residual + LayerNorm launches):
+//   moments of the fp32 rows, stats[split][64][2] = (sum x, sum x^2) over the split's k-range, next to the partials
+struct LnFoldStats {
+  const float *stats;  // NULL: the partials are plain (no folded LayerNorm)
+  const float *c;      // [N]  sum_k wf[n,k]
+  int splits, d;       // splits of the producing projection, LayerNorm width
+  float eps;
+};
+__device__ __forceinline__ void ln_fold_moments(const LnFoldStats &f, int b, float &mean, float &rstd) {
+  // every split's pair requested before the first one is used (one L2 round trip, not `splits` of them)
+  float2 m[kMaxForcedSplits];
+#pragma unroll
+  for (int s = 0; s < kMaxForcedSplits; ++s)
+    m[s] = s < f.splits ? __ldcg(reinterpret_cast<const float2 *>(f.stats + ((int64_t)s * 64 + b) * 2))
+                        : make_float2(0.f, 0.f);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int s = 0; s < kMaxForcedSplits; ++s) {
+    s1 += m[s].x;
+    s2 += m[s].y;
+  }
+  mean = s1 / (float)f.d;
+  rstd = rsqrtf(fmaxf(s2 / (float)f.d - mean * mean, 0.f) + f.eps);
+}
+int launch_gemm_decode_x(const float *x, int B, int64_t ldx, const bf16 *Wf, int N, int K, int force_splits,
+                         float *partials, size_t partial_bytes, float *stats, int *out_splits, int *out_ldp,
+                         const KvPrefetch *pf, bool pdl, cudaStream_t s);
+int launch_ln_fold(const bf16 *W, int N, int K, const float *gamma, const float *beta, const float *bias, bf16 *wf,
+                   float *c, float *dvec, cudaStream_t s);
 
 // attention.cu
 int launch_attention_varlen(const void *qkv, int dtype, int64_t M, int B, int n_head, int head_dim,
@@ -159,11 +188,11 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
                        int B, int n_head, int head_dim, void *kcache, void *vcache, int dtype,
                        int64_t cache_seq_stride, int cache_cap, const int32_t *text_len, const int32_t *prompt_len,
                        const int32_t *n_gen, const int32_t *finished, float *out, void *out16, void *workspace,
-                       bool pdl, cudaStream_t s);
+                       bool pdl, cudaStream_t s, const LnFoldStats *fold = nullptr);
 
 // decode_fused.cu
 int launch_relu_reduce(const float *partials, int splits, int ldp, const float *bias, int B, int N, bf16 *out16,
-                       int64_t ldo, bool pdl, cudaStream_t s);
+                       int64_t ldo, bool pdl, cudaStream_t s, const LnFoldStats *fold = nullptr);
 int launch_ln_reduce(float *x, int64_t ldx, int B, int d, const float *partials, int splits, int ldp,
                      const float *bias, const float *gamma, const float *beta, float eps, bf16 *out16,
                      bool pdl, cudaStream_t s);
@@ -185,6 +214,6 @@ int launch_cast_from_f32(const float *in, void *out, int dtype, int64_t n, cudaS
 // sample.cu
 int launch_ar_sample(float *logits, int64_t ld_logits, const float *partials, int splits, int ldp,
                      const vb_ar_head *head, vb_ar_state *st, int d, const int64_t *forced, int reduce_only, bool pdl,
-                     cudaStream_t s);
+                     cudaStream_t s, const LnFoldStats *fold = nullptr);
 
 }  // namespace vb

@@ -39,7 +39,7 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
                  const int32_t *__restrict__ prompt_len, const int32_t *__restrict__ max_new,
                  int32_t *__restrict__ n_gen, int32_t *__restrict__ finished,
                  int32_t *__restrict__ tokens, int tok_stride, float *__restrict__ x_cur, int d,
-                 const int64_t *__restrict__ forced, int reduce_only) {
+                 const int64_t *__restrict__ forced, int reduce_only, LnFoldStats fold, const float *__restrict__ fold_d) {
   __shared__ ArgMax wbest[8];
   __shared__ int s_tok, s_pos;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -59,6 +59,10 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
   const int forced_tok = forced ? (int)forced[b] : -1;
   float *row = logits + (int64_t)b * ld_logits;
   ArgMax best{-CUDART_INF_F, 0x7fffffff};
+  // final LayerNorm folded into ar_predict_layer (gemm_decode_x_kernel): logit = rstd (acc - mean c[i]) + (beta W^T)[i]
+  float f_mean = 0.f, f_rstd = 1.f;
+  const bool folded = fold.stats != nullptr && partials != nullptr;
+  if (folded) ln_fold_moments(fold, b, f_mean, f_rstd);
   if (partials && n_vocab <= 5 * 256 && splits <= 8) {
     // head projection split-K partials, summed in fixed order; all loads of the row issued at once
     float v[5][8];
@@ -77,6 +81,7 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
       for (int s = 1; s < 8; ++s)
         if (s < splits) a += v[j][s];
       if (i < n_vocab) {
+        if (folded) a = f_rstd * (a - f_mean * fold.c[i]) + fold_d[i];
         row[i] = a;
         best = better(best, ArgMax{a, i});
       }
@@ -89,6 +94,7 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
         v = __ldcg(p);
 #pragma unroll 8
         for (int s = 1; s < splits; ++s) v += __ldcg(p + (int64_t)s * 64 * ldp);
+        if (folded) v = f_rstd * (v - f_mean * fold.c[i]) + fold_d[i];
         row[i] = v;
       } else {
         v = row[i];
@@ -141,11 +147,15 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
 
 int launch_ar_sample(float *logits, int64_t ld_logits, const float *partials, int splits, int ldp,
                      const vb_ar_head *head, vb_ar_state *st, int d, const int64_t *forced, int reduce_only, bool pdl,
-                     cudaStream_t s) {
+                     cudaStream_t s, const LnFoldStats *fold) {
+  LnFoldStats f{};
+  if (fold) f = *fold;
+  const float *fold_d = fold ? head->fold.dvec : nullptr;
   VB_CUDA(launch_kernel(ar_sample_kernel, dim3(st->B), dim3(256), 0, s, pdl, logits, ld_logits, partials, splits, ldp,
                         head->n_vocab, head->eos_id, head->audio_emb, head->alpha, head->pe, head->pe_rows,
                         (const int32_t *)st->text_len, (const int32_t *)st->prompt_len, (const int32_t *)st->max_new,
-                        st->n_gen, st->finished, st->tokens, st->tok_stride, st->x_cur, d, forced, reduce_only));
+                        st->n_gen, st->finished, st->tokens, st->tok_stride, st->x_cur, d, forced, reduce_only, f,
+                        fold_d));
   count_launch();
   return VB_OK;
 }

@@ -145,6 +145,28 @@ inline int make_tmap_2d(CUtensorMap *map, const void *ptr, int64_t rows, int64_t
   }
   return VB_OK;
 }
+// row-major fp32 [rows, cols] matrix, dense (un-swizzled) box of [box_rows, box_cols] floats; rows past `rows` read as 0
+inline int make_tmap_f32_dense(CUtensorMap *map, const void *ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                               int box_cols) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("tensor map: cuTensorMapEncodeTiled entry point unavailable");
+    return VB_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tensor map: cuTensorMapEncodeTiled (fp32 dense) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+              (long long)rows, (long long)cols, (long long)ld);
+    return VB_ERR_CUDA;
+  }
+  return VB_OK;
+}
 // TMA stores from a 128B-swizzled shared-memory box (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),

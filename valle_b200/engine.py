@@ -18,6 +18,8 @@ libvalle_b200.so.  There is no CPU fallback.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -140,6 +142,8 @@ class ValleEngine:
         self.last_packed: Optional[torch.Tensor] = None
         #: rows of one tensor-core decode group (gemm_decode.cu: one UMMA N tile); larger bf16 batches are split
         self.max_tc_batch = 64
+        #: bf16 decode steps run the LayerNorm-folded chain (6 launches per layer instead of 8)
+        self.use_decode_fold = os.environ.get("VB_DECODE_FOLD", "1") != "0"
         #: greedy decode steps captured per CUDA graph (one replay per group; the stop flags are polled every `poll` steps)
         self.steps_per_graph = 8
         self.replayed_launches = 0   # kernels executed through CUDA-graph replays
@@ -164,6 +168,12 @@ class ValleEngine:
         cast = (lambda t: t.detach().to(self.dtype).contiguous()) if self.dtype != torch.float32 \
             else (lambda t: t.detach())
         self.ar_predict_w = cast(m.ar_predict_layer.weight)
+        # bf16 decode chain: LayerNorms folded into the projections that consume them (vb_ln_fold), incl. the final norm
+        # into ar_predict_layer (valle.py:1039)
+        self.ar_head_fold = None
+        fn = m.ar_decoder.norm
+        if self.dtype == torch.bfloat16 and self.use_decode_fold and fn is not None and self.ar.enable_decode_fold():
+            self.ar_head_fold = self.ar.fold_layernorm(self.ar_predict_w, fn.weight.detach(), fn.bias.detach(), None)
         self.nar_predict_w = [cast(l.weight) for l in m.nar_predict_layers] if self.Q > 1 else []
         self._ada_cache = None
         self._bufs.clear()  # graphs hold stale weight pointers
@@ -242,6 +252,8 @@ class ValleEngine:
         h.alpha = m.ar_audio_position.alpha.detach().data_ptr()
         h.pe, h.pe_rows = pe.data_ptr(), pe.shape[0]
         h.greedy = int(greedy)
+        if self.ar_head_fold is not None:
+            h.fold = self.ar_head_fold
         return h
 
     def _buffers(self, B: int, cap: int, tok_stride: int) -> _ArBuffers:

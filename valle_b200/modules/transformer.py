@@ -254,6 +254,7 @@ class NativeDecoder:
             raise L.VbError("valle_b200: the model must live on a CUDA device (no CPU fallback)")
         self.device = dev
         self._keep = []
+        self._bf16 = {}   # data_ptr -> packed bf16 copy of a big matrix
         self._sig = self._signature()
 
         def big(p):
@@ -262,6 +263,7 @@ class NativeDecoder:
                 raise L.VbError("valle_b200: parameters must be contiguous fp32")
             if dtype == torch.bfloat16:
                 t = t.to(torch.bfloat16).contiguous()
+                self._bf16[t.data_ptr()] = t
             self._keep.append(t)
             return t.data_ptr()
 
@@ -311,6 +313,41 @@ class NativeDecoder:
 
     def _signature(self):
         return tuple((p.data_ptr(), p._version) for p in self.enc.parameters())
+
+    def fold_layernorm(self, w16: Tensor, gamma: Tensor, beta: Tensor, bias: Optional[Tensor]) -> "L.LnFold":
+        """vb_ln_fold_build: LayerNorm(gamma, beta) folded into the bf16 projection w16 [N, K] (+ bias) that consumes
+        it -- wf = w16 * gamma, c = row sums of wf, dvec = bias + w16 @ beta (include/valle_b200.h vb_ln_fold)"""
+        N, K = w16.shape
+        wf = torch.empty_like(w16)
+        c = torch.empty(N, dtype=torch.float32, device=w16.device)
+        dv = torch.empty(N, dtype=torch.float32, device=w16.device)
+        with torch.cuda.device(self.device):
+            L.check(self.lib.vb_ln_fold_build(w16.data_ptr(), N, K, gamma.data_ptr(), beta.data_ptr(), L.ptr(bias),
+                                              wf.data_ptr(), c.data_ptr(), dv.data_ptr(), L.stream_ptr()),
+                    "vb_ln_fold_build")
+        self._keep += [wf, c, dv]
+        f = L.LnFold()
+        f.wf, f.c, f.dvec = wf.data_ptr(), c.data_ptr(), dv.data_ptr()
+        return f
+
+    def enable_decode_fold(self) -> bool:
+        """bf16 AR decode chain without the residual + LayerNorm launches (valle/modules/transformer.py:296-302): norm1
+        is folded into in_proj and norm2 into linear1 of every layer (plain LayerNorm only).  Returns False (chain left
+        as it is) for fp32 storage and for AdaptiveLayerNorm stacks."""
+        if self.dtype != torch.bfloat16 or self.adaptive:
+            return False
+        qkv = (L.LnFold * self.n_layer)()
+        ffn1 = (L.LnFold * self.n_layer)()
+        for i, lyr in enumerate(self.enc.layers):
+            a = self._layers[i]
+            w_in = self._bf16[a.in_proj_w]
+            w_l1 = self._bf16[a.lin1_w]
+            qkv[i] = self.fold_layernorm(w_in, lyr.norm1.weight.detach(), lyr.norm1.bias.detach(),
+                                         lyr.self_attn.in_proj_bias.detach())
+            ffn1[i] = self.fold_layernorm(w_l1, lyr.norm2.weight.detach(), lyr.norm2.bias.detach(),
+                                          lyr.linear1.bias.detach())
+        L.check(self.lib.vb_decoder_set_decode_fold(self.handle, qkv, ffn1), "vb_decoder_set_decode_fold")
+        return True
 
     def stale(self) -> bool:
         return self._sig != self._signature()
