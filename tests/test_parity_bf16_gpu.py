@@ -296,3 +296,61 @@ def test_bf16_batches_above_64_are_decoded_in_tensor_core_groups():
     ref = eng.generate(texts[:4], prompts[:4], top_k=1, max_new_tokens=12)
     for i in range(70):
         assert torch.equal(out[i].cpu(), ref[i % 4]), i
+
+
+# ---------------------------------------------------------------- LayerNorm-folded decode chain (vb_ln_fold)
+def test_ln_fold_build_matches_its_definition():
+    """vb_ln_fold_build: wf = bf16(W * gamma), c = row sums of wf, dvec = bias + W @ beta (include/valle_b200.h)"""
+    import ctypes as C
+    from valle_b200 import _lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(11)
+    N, K = 300, 256
+    W = (torch.randn(N, K, generator=g) / 16).bfloat16()
+    gamma, beta, bias = 1 + 0.1 * torch.randn(K, generator=g), 0.1 * torch.randn(K, generator=g), torch.randn(N, generator=g)
+    Wd, gd, bd, biasd = W.to(DEV), gamma.to(DEV), beta.to(DEV), bias.to(DEV)
+    wf = torch.empty_like(Wd)
+    c = torch.empty(N, device=DEV)
+    dv = torch.empty(N, device=DEV)
+    L.check(lib.vb_ln_fold_build(Wd.data_ptr(), N, K, gd.data_ptr(), bd.data_ptr(), biasd.data_ptr(), wf.data_ptr(),
+                                 c.data_ptr(), dv.data_ptr(), L.stream_ptr()))
+    torch.cuda.synchronize()
+    wf_ref = (W.float() * gamma).bfloat16()
+    assert torch.equal(wf.cpu(), wf_ref)
+    assert torch.allclose(c.cpu(), wf_ref.float().sum(1), atol=1e-4, rtol=1e-5)
+    assert torch.allclose(dv.cpu(), bias + W.float() @ beta, atol=1e-4, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["tiny_batch.pt", "big_short.pt"])
+def test_folded_decode_chain_matches_the_unfolded_chain(name):
+    """The bf16 decode step with the LayerNorms folded into the projections (6 launches per layer: fp32-fed
+    projections carrying the rows' moments, residual stream assembled by bulk reductions) against the chain with the
+    separate residual + LayerNorm launches on the same weights: per-step logits within 2e-2 (both round to bf16 at
+    different points), the same early greedy ids, and the folded chain is what the engine runs by default."""
+    from valle_b200 import _lib as L
+    lib = L.load()
+    g = load_golden(name)
+    m = _model(g, torch.bfloat16)
+    eng = m.engine()
+    assert eng.ar_head_fold is not None, "the LayerNorm-folded chain must be on by default in bf16"
+    if "utts" in g:
+        texts = [u["x"][0] for u in g["utts"]] * 3
+        prompts = [u["y"][0] for u in g["utts"]] * 3
+    else:
+        texts, prompts = [g["x"][0]] * 3, [g["y"][0]] * 3
+    steps = {0, 1, 2, 7, 15}
+    tr_f = {"steps": steps}
+    out_f = eng.generate(texts, prompts, top_k=1, trace=tr_f, max_new_tokens=16)
+    L.check(lib.vb_tune_set(b"VB_DECODE_FOLD", 0))
+    try:
+        eng._bufs.clear()
+        tr_u = {"steps": steps}
+        out_u = eng.generate(texts, prompts, top_k=1, trace=tr_u, max_new_tokens=16)
+    finally:
+        L.check(lib.vb_tune_set(b"VB_DECODE_FOLD", 1))
+        eng._bufs.clear()
+    for s in sorted(steps):
+        err = (tr_f["ar_logits"][s] - tr_u["ar_logits"][s]).abs().max().item()
+        assert err < 2e-2, (s, err)
+    agree = sum(int((a[:6, 0] == b[:6, 0]).all()) for a, b in zip(out_f, out_u))
+    assert agree >= len(out_f) - 1, agree

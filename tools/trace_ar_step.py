@@ -52,6 +52,14 @@ def main():
     for t, k in ev:
         if k & 1:
             ends.setdefault(k >> 1, []).append(t)
+    # block 0's own end stamp that follows each start stamp of the same kernel kind (its duration inside the stage)
+    own = {}
+    pend = {}
+    for t, k in ev:
+        if (k & 1) == 0:
+            pend[k >> 1] = t
+        elif (k >> 1) in pend:
+            own[pend.pop(k >> 1)] = t      # keyed by the start stamp
     idx = [i for i, (_, k) in enumerate(starts) if k == 5]
     steps_ev = [starts[idx[j] + 1: idx[j + 1] + 1] for j in range(len(idx) - 1)]
     steps_ev = [s for s in steps_ev if len(s) > 10]
@@ -76,11 +84,17 @@ def main():
         agg.setdefault(nm, []).append(v)
     for nm, vs in agg.items():
         print(f"  {nm:14s} n={len(vs):3d}  mean {sum(vs) / len(vs):6.2f} us  total {sum(vs):7.1f} us ({100 * sum(vs) / total:4.1f} %)")
+    # block 0: time from its dependency wait to its own end (the rest of the stage = the grid's tail + the hand-over)
+    own_stats = []
+    for p in range(L0 - 1):
+        d = [own[s[p][0]] - s[p][0] for s in steps_ev if s[p][0] in own]
+        own_stats.append(sum(d) / len(d) / 1000.0 if d else float("nan"))
     if per_layer:
-        print(f"per-layer chain ({per_layer} kernels), mean over 12 layers:")
+        print(f"per-layer chain ({per_layer} kernels), mean over 12 layers: stage us | block 0 wait->end us")
         for j in range(per_layer):
             vs = [pos_stats[l * per_layer + j][1] for l in range(12)]
-            print(f"  [{j}] {pos_stats[j][0]:14s} {sum(vs) / 12:6.2f} us")
+            os_ = [own_stats[l * per_layer + j] for l in range(12)]
+            print(f"  [{j}] {pos_stats[j][0]:14s} {sum(vs) / 12:6.2f} us | {sum(os_) / 12:6.2f}")
     if out:
         json.dump(dict(B=B, frames=frames, ar_ms=ar_ms, steps=steps, kernels_per_step=L0,
                        stage_us=[dict(kernel=nm, us=v) for nm, v in pos_stats]), open(out, "w"), indent=1)

@@ -434,7 +434,7 @@ StepWs carve_step_ws(const vb_decoder_desc &D, int B, int cache_cap, void *base)
   w.hb16 = (bf16 *)take((size_t)64 * dff * 2);
   w.gemm_ws_bytes = gemm_decode_workspace((int)d, (int)dff);
   w.gemm_ws = take(w.gemm_ws_bytes);
-  w.stats = (float *)take((size_t)kMaxForcedSplits * 64 * 2 * sizeof(float));
+  w.stats = (float *)take((size_t)kLnFoldMaxCopies * kMaxForcedSplits * 64 * 2 * sizeof(float));
   w.total = (size_t)(p - (char *)base) + 256;
   return w;
 }
@@ -465,10 +465,10 @@ int tc_head(vb_decoder *dec, const vb_ar_head *head, float *x, vb_ar_state *st, 
   const bool pdl = use_pdl();
   if (head->fold.wf && pend.part == nullptr && tune("VB_DECODE_FOLD", 1) != 0) {
     // final LayerNorm folded into ar_predict_layer: the projection reads the fp32 rows, the sampler applies the moments
-    int sp = 1, ldp = 0;
+    int sp = 1, ldp = 0, cp = 1;
     VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)head->fold.wf, head->n_vocab, d, 0, (float *)w.gemm_ws,
-                                w.gemm_ws_bytes, w.stats, &sp, &ldp, nullptr, pdl, s));
-    const LnFoldStats fs{w.stats, head->fold.c, sp, d, 1e-5f};
+                                w.gemm_ws_bytes, w.stats, &sp, &ldp, &cp, nullptr, pdl, s));
+    const LnFoldStats fs{w.stats, head->fold.c, sp, d, 1e-5f, cp};
     return launch_ar_sample(st->logits, ldl, (const float *)w.gemm_ws, sp, ldp, head, st, d, nullptr,
                             head->greedy ? 0 : 1, pdl, s, &fs);
   }
@@ -567,6 +567,10 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
       const int qkv_f = qkv_env > 0 ? qkv_env : std::max(1, std::min(5, d / 128));
       const int ffn1_f = ffn1_env > 0 ? ffn1_env : std::max(1, std::min(4, d / 128));
       const int out_f = out_splits > 0 ? out_splits : 8;
+      // (linear1 + ReLU in one launch -- the splits of a tile as a thread-block cluster reducing over DSMEM -- measured
+      //  slower: 9.5 + 8.2 us for FFN1 + FFN2 against 5.0 + 4.9 + 6.6 us with the separate reduce launch)
+      const bool relu_in_cluster = tune("VB_FFN1_CLUSTER", 0) != 0;
+      const bool dbg_nomom = tune("VB_FOLD_DEBUG_NOMOM", 0) != 0;   // timing experiment only (wrong numerics)
       for (int l = 0; l < D.n_layer; ++l) {
         const vb_layer_params &L = dec->layers[l];
         const vb_ln_fold &Fq = dec->fold_qkv[l], &Ff = dec->fold_ffn1[l];
@@ -574,20 +578,26 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
                          pf_f2 = kv_slice(l + 1, 2);
         void *kc = (char *)st->kcache + (size_t)l * st->cache_layer_stride * ts;
         void *vc = (char *)st->vcache + (size_t)l * st->cache_layer_stride * ts;
-        int s1 = 1, ldp1 = 0;
+        int s1 = 1, ldp1 = 0, cp1 = 1;
         VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)Fq.wf, 3 * d, d, qkv_f, P, w.gemm_ws_bytes, w.stats, &s1, &ldp1,
-                                    &pf_qkv, pdl, s));
-        const LnFoldStats fq{w.stats, Fq.c, s1, d, 1e-5f};
+                                    &cp1, &pf_qkv, pdl, s));
+        const LnFoldStats fq{w.stats, Fq.c, dbg_nomom ? 0 : s1, d, 1e-5f, cp1};
         VB_TRY(launch_attn_decode(w.q, P, s1, ldp1, Fq.dvec, B, D.n_head, hd, kc, vc, dt, st->cache_seq_stride,
                                   st->cache_cap, st->text_len, st->prompt_len, st->n_gen, st->finished, w.att, w.att16,
                                   w.attn_ws, pdl, s, &fq));
         VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)L.out_proj_w, d, d, out_f, L.out_proj_b, DG_RESIDUAL, x,
                                   nullptr, d, nullptr, nullptr, 0, nullptr, nullptr, &pf_out, pdl, s, true));
-        int sf = 1, ldpf = 0;
-        VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)Ff.wf, dff, d, ffn1_f, P, w.gemm_ws_bytes, w.stats, &sf, &ldpf,
-                                    &pf_f1, pdl, s));
-        const LnFoldStats ff{w.stats, Ff.c, sf, d, 1e-5f};
-        VB_TRY(launch_relu_reduce(P, sf, ldpf, Ff.dvec, B, dff, w.hb16, dff, pdl, s, &ff));
+        if (relu_in_cluster) {   // linear1 + ReLU in one launch: the splits of a tile reduce over DSMEM
+          const XRelu xr{Ff.c, Ff.dvec, 1e-5f, w.hb16, dff};
+          VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)Ff.wf, dff, d, ffn1_f, nullptr, 0, nullptr, nullptr, nullptr,
+                                      nullptr, &pf_f1, pdl, s, &xr));
+        } else {
+          int sf = 1, ldpf = 0, cpf = 1;
+          VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)Ff.wf, dff, d, ffn1_f, P, w.gemm_ws_bytes, w.stats, &sf,
+                                      &ldpf, &cpf, &pf_f1, pdl, s));
+          const LnFoldStats ff{w.stats, Ff.c, dbg_nomom ? 0 : sf, d, 1e-5f, cpf};
+          VB_TRY(launch_relu_reduce(P, sf, ldpf, Ff.dvec, B, dff, w.hb16, dff, pdl, s, &ff));
+        }
         VB_TRY(launch_gemm_decode(w.hb16, B, dff, (const bf16 *)L.lin2_w, d, dff, ffn2_splits, L.lin2_b, DG_RESIDUAL, x,
                                   nullptr, d, nullptr, nullptr, 0, nullptr, nullptr, &pf_f2, pdl, s, true));
       }

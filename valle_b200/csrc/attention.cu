@@ -323,7 +323,7 @@ attn_decode_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *_
         for (int s = 1; s < qp.splits; ++s) acc += __ldcg(p + (int64_t)s * 64 * qp.ldp);
         if (qp.fold.stats) {
           float mean, rstd;
-          ln_fold_moments(qp.fold, b, mean, rstd);
+          ln_fold_moments(qp.fold, b, h, mean, rstd);
           acc = rstd * (acc - mean * qp.fold.c[col]);
         }
         a[j] = acc + qp.bias[col];
@@ -443,13 +443,18 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
                    const int32_t *__restrict__ n_gen, const int32_t *__restrict__ finished,
                    float *__restrict__ out, bf16 *__restrict__ out16,
                    float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit) {
-  __shared__ float sc[kDecMaxChunk];
+  // score buffer of the chunk: dynamic shared memory sized by the launch (cache_cap / nsplit keys), so that the
+  // kernel's footprint -- and with it the shared-memory carve-out the driver picks, i.e. how much L1 is left to land
+  // the ~110 KB of K / V loads an SM keeps in flight -- follows the actual context instead of the 4096-key maximum
+  extern __shared__ float sc[];
   __shared__ __align__(16) float qs[HD];
   __shared__ __align__(16) float knew[HD];
   __shared__ __align__(16) float vnew[HD];
   __shared__ float red[16][HD + 1];
   __shared__ float wred[8];
+  __shared__ float pex[3][HD];
   pdl_launch_dependents();
+  vb_trace_cta(16);   // CTA resident
   const int h = blockIdx.x, b = blockIdx.y, sp = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = n_head * HD;
@@ -491,33 +496,44 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
   }
   pdl_wait();
   vb_trace(TR_ATTN * 2);
+  vb_trace_cta(17);   // dependency resolved
   if (decode_row_finished(finished, b, h, sp, d, tid, nsplit, n_head, out, out16, part_o, part_ml)) return;
   int n_gen_now;
   asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(n_gen_now) : "l"(n_gen + b) : "memory");
   if (n_gen_now != n_gen_early) setup(n_gen_now);  // uniform over the CTA
-  if (tid < HD) {
-    if (has_new) {
+  if (has_new) {
+    // q / k / v of the current token = sum of the projection's split-K partial tiles (+ folded LayerNorm, bias).  All 128
+    // threads fetch: thread = (column c of the head, parity of the split), <= 3 splits x 3 columns each in ONE round
+    // trip; the odd half hands its sums over through shared memory.  (A per-thread loop over the splits costs one
+    // dependent L2 round trip per split.)
+    const int c = tid & (HD - 1), hf = tid >> 6;
+    float2 mraw = make_float2(0.f, 0.f);
+    if (qp.fold.stats && hf == 0) mraw = ln_fold_moments_load(qp.fold, b, h);   // warps 0 and 1, complete
+    float pv[3][3];   // (<= 6 splits in the one round trip; the chain uses 5)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float *p = qp.part + (int64_t)b * qp.ldp + j * d + h * HD + c;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int s = hf + 2 * k;
+        pv[j][k] = s < qp.splits ? __ldcg(p + (int64_t)s * 64 * qp.ldp) : 0.f;
+      }
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (qp.fold.stats && hf == 0) ln_fold_moments_finish(qp.fold, mraw, mean, rstd);
+    float acc[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      acc[j] = (pv[j][0] + pv[j][1]) + pv[j][2];
+      const float *p = qp.part + (int64_t)b * qp.ldp + j * d + h * HD + c;
+      for (int s = 6 + hf; s < qp.splits; s += 2) acc[j] += __ldcg(p + (int64_t)s * 64 * qp.ldp);
+      if (hf == 1) pex[j][c] = acc[j];
+    }
+    __syncthreads();
+    if (hf == 0) {
       float a[3];
-      // all partial sums of the three columns (and the rows' moments) requested in one round trip
-      constexpr int kU = 8;
-      float pv[3][kU];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float *p = qp.part + (int64_t)b * qp.ldp + j * d + h * HD + tid;
-#pragma unroll
-        for (int s = 0; s < kU; ++s) pv[j][s] = s < qp.splits ? __ldcg(p + (int64_t)s * 64 * qp.ldp) : 0.f;
-      }
-      float mean = 0.f, rstd = 1.f;
-      if (qp.fold.stats) ln_fold_moments(qp.fold, b, mean, rstd);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        float acc = pv[j][0];
-#pragma unroll
-        for (int s = 1; s < kU; ++s) acc += pv[j][s];   // fixed order 0..S-1 (the tail adds exact zeros)
-        const float *p = qp.part + (int64_t)b * qp.ldp + j * d + h * HD + tid;
-        for (int s = kU; s < qp.splits; ++s) acc += __ldcg(p + (int64_t)s * 64 * qp.ldp);
-        a[j] = rstd * (acc - mean * qc[j]) + qbias[j];
-      }
+      for (int j = 0; j < 3; ++j) a[j] = rstd * ((acc[j] + pex[j][c]) - mean * qc[j]) + qbias[j];
       qs[tid] = a[0] * 0.125f;
       const T k16 = from_f32<T>(a[1]), v16 = from_f32<T>(a[2]);
       knew[tid] = to_f32(k16);  // exactly what later steps will read back from the cache
@@ -526,9 +542,9 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
         kb[(int64_t)pos * HD + tid] = k16;
         vb_[(int64_t)pos * HD + tid] = v16;
       }
-    } else {
-      qs[tid] = q[(int64_t)b * d + h * HD + tid] * 0.125f;
     }
+  } else if (tid < HD) {
+    qs[tid] = q[(int64_t)b * d + h * HD + tid] * 0.125f;
   }
   __syncthreads();
 
@@ -538,6 +554,8 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
   for (int i = 0; i < 8; ++i) qf[i] = qs[j8 + i];
   float lmax = -CUDART_INF_F;
   const bool new_here = has_new && pos >= c0 && pos < c1;  // the current token's key lives in smem
+  // (refilling the registers of a half batch with the next batch's rows as soon as that half is consumed -- loads always
+  //  in flight per warp -- measured the same: CTA duration 15.2 vs 15.3 us, profiles/round2_summary.md)
   for (int base = 0; base < n; base += 16 * U) {
     if (base > 0) {
 #pragma unroll
@@ -646,6 +664,7 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
     }
   }
   vb_trace(TR_ATTN * 2 + 1);
+  vb_trace_cta(18);   // CTA done
 }
 
 __global__ void attn_decode_combine_kernel(const float *__restrict__ part_o,
@@ -698,6 +717,13 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
   float *part_ml = part_o + (size_t)B * n_head * ns * HD;
   QkvPartials qp{qkv_part, qkv_bias, qkv_splits, qkv_ldp, LnFoldStats{}};
   if (fold) qp.fold = *fold;
+  static PerDeviceOnce once;
+  if (once.first()) {
+    prefer_chain_carveout(attn_decode_kernel<float>);
+    prefer_chain_carveout(attn_decode_kernel<bf16>);
+    prefer_chain_carveout(attn_decode_2phase_pf_kernel<8>);
+    prefer_chain_carveout(attn_decode_combine_kernel);
+  }
   dim3 grid(n_head, B, ns);
   if (dtype == VB_F32 || getenv("VB_ATTN_DECODE_1PASS") != nullptr) {  // fp32 parity path / single-pass variant
     if (dtype == VB_F32)
@@ -709,9 +735,30 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
                             (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, finished, out,
                             (bf16 *)out16, part_o, part_ml, ns));
   } else {
-    VB_CUDA(launch_kernel(attn_decode_2phase_pf_kernel<8>, grid, dim3(128), 0, s, pdl, q, qp, n_head, (bf16 *)kcache,
-                          (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen, finished, out,
-                          (bf16 *)out16, part_o, part_ml, ns));
+    // score buffer: the chunk of one split, rounded as the kernel rounds it (+16), in 1 KB steps
+    const size_t sc_bytes = align_up((size_t)((cache_cap + ns - 1) / ns + 32) * sizeof(float), 1024);
+    // VB_ATTN_CARVEOUT: shared-memory carve-out (percent) preferred for this kernel; -1 = the driver's choice.  72 % =
+    // the 164 KB partition the projections of the chain run with: the driver's own pick for this (small) footprint
+    // measured 1.5-3 % slower over the AR phase (the SMs re-partition on the way in and out of every attention launch),
+    // the largest carve-out 25 % slower per launch (no L1 left for the loads in flight)
+    static int carve_set[64];
+    static bool carve_init = false;
+    if (!carve_init) {
+      for (int i = 0; i < 64; ++i) carve_set[i] = -2;
+      carve_init = true;
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int carve = tune("VB_ATTN_CARVEOUT", 72);
+    if (carve_set[dev & 63] != carve) {
+      const int want = carve >= 0 ? carve : (int)cudaSharedmemCarveoutDefault;
+      if (carve >= 0 || carve_set[dev & 63] != -2)
+        VB_CUDA(cudaFuncSetAttribute(attn_decode_2phase_pf_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, want));
+      carve_set[dev & 63] = carve;
+    }
+    VB_CUDA(launch_kernel(attn_decode_2phase_pf_kernel<8>, grid, dim3(128), sc_bytes, s, pdl, q, qp, n_head,
+                          (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen,
+                          finished, out, (bf16 *)out16, part_o, part_ml, ns));
   }
   count_launch();
   if (ns > 1) {

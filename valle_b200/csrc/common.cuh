@@ -223,6 +223,15 @@ struct PerDeviceOnce {
   }
 };
 
+// Experiment knob: VB_CHAIN_CARVEOUT = percentage makes every kernel of the PDL-chained decode step prefer the same
+// shared-memory / L1 partition of the SM.  Measured (profiles/round2_summary.md): forcing the largest carve-out slows
+// the KV-cache attention from 25.7 to 32.1 us per launch -- its ~110 KB of loads in flight per SM need the L1 lines --
+// so the default (-1) leaves the driver's per-kernel choice (164 KB for the projections and the attention alike).
+template <typename K> inline void prefer_chain_carveout(K kern) {
+  const int pct = tune("VB_CHAIN_CARVEOUT", -1);
+  if (pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 // ---- device timeline (profiling builds only: -DVB_TRACE, libvalle_b200_trace.so) ----------------
 // Thread 0 of block (0,0,0) of a traced kernel appends (globaltimer << 8 | id) to a ring bound with
 // vb_trace_bind() (the ring keeps the most recent `cap` stamps); ids: kernel kind * 2 + (0 = dependency resolved, 1 = block 0 done).
@@ -230,8 +239,20 @@ struct PerDeviceOnce {
 static __device__ unsigned long long *g_trace_buf = nullptr;
 static __device__ unsigned int *g_trace_cnt = nullptr;
 static __device__ unsigned int g_trace_cap = 0;
+static __device__ unsigned int g_trace_all = 0;   // 1: only vb_trace_cta stamps (every CTA of the traced kernel)
+// every CTA's thread 0: (low 40 bits of globaltimer << 24) | (linear block id, 16 bits) << 8 | id  (tools/trace_attn_ctas.py)
+__device__ __forceinline__ void vb_trace_cta(int id) {
+  if (threadIdx.x == 0 && g_trace_all != 0 && g_trace_buf != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const unsigned i = atomicAdd(g_trace_cnt, 1u);
+    g_trace_buf[i % g_trace_cap] = ((t & ((1ull << 40) - 1)) << 24) | ((unsigned long long)(bid & 0xffff) << 8) |
+                                   (unsigned long long)(id & 0xff);
+  }
+}
 __device__ __forceinline__ void vb_trace(int id) {
-  if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0 && g_trace_buf != nullptr) {
+  if ((blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0 && g_trace_buf != nullptr && g_trace_all == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     const unsigned i = atomicAdd(g_trace_cnt, 1u);
@@ -243,7 +264,10 @@ void trace_register(trace_bind_fn f);
 static int trace_bind_tu(unsigned long long *buf, unsigned int *cnt, unsigned int cap) {
   if (cudaMemcpyToSymbol(g_trace_buf, &buf, sizeof(buf)) != cudaSuccess) return 1;
   if (cudaMemcpyToSymbol(g_trace_cnt, &cnt, sizeof(cnt)) != cudaSuccess) return 1;
+  const unsigned int all = cap >> 31;   // top bit of the capacity: per-CTA stamps of the attention kernel only
+  cap &= 0x7fffffffu;
   if (cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(g_trace_all, &all, sizeof(all)) != cudaSuccess) return 1;
   return 0;
 }
 namespace {
@@ -254,6 +278,7 @@ static TraceReg g_trace_reg;
 }  // namespace
 #else
 #define vb_trace(id) ((void)0)
+#define vb_trace_cta(id) ((void)0)
 #endif
 enum { TR_LN = 1, TR_GEMM = 2, TR_ATTN = 3, TR_RELU = 4, TR_SAMPLE = 5, TR_COMBINE = 6, TR_FUSED = 7 };
 

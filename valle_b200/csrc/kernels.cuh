@@ -144,26 +144,41 @@ struct LnFoldStats {
   const float *c;      // [N]  sum_k wf[n,k]
   int splits, d;       // splits of the producing projection, LayerNorm width
   float eps;
+  int copies;          // every tile row of the producing grid stores its own copy of the moments:
+                       // stats[copy][split][64][2]; consumers spread over the copies (no L2 hot spot)
 };
-__device__ __forceinline__ void ln_fold_moments(const LnFoldStats &f, int b, float &mean, float &rstd) {
-  // every split's pair requested before the first one is used (one L2 round trip, not `splits` of them)
-  float2 m[kMaxForcedSplits];
-#pragma unroll
-  for (int s = 0; s < kMaxForcedSplits; ++s)
-    m[s] = s < f.splits ? __ldcg(reinterpret_cast<const float2 *>(f.stats + ((int64_t)s * 64 + b) * 2))
-                        : make_float2(0.f, 0.f);
-  float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-  for (int s = 0; s < kMaxForcedSplits; ++s) {
-    s1 += m[s].x;
-    s2 += m[s].y;
-  }
-  mean = s1 / (float)f.d;
-  rstd = rsqrtf(fmaxf(s2 / (float)f.d - mean * mean, 0.f) + f.eps);
+constexpr int kLnFoldMaxCopies = 32;
+// Called by every lane of a (converged) warp whose threads share the row b: lane s fetches split s's pair, the warp
+// adds them up by shuffles -- ONE L2 round trip.  (A per-thread loop over the splits, however it is unrolled, ends up
+// as `splits` dependent round trips under the register caps of the consumer kernels: 2.3 us in the attention prologue.)
+__device__ __forceinline__ float2 ln_fold_moments_load(const LnFoldStats &f, int b, int which) {
+  const int lane = threadIdx.x & 31;
+  const float *st = f.stats + (int64_t)(which % f.copies) * f.splits * 64 * 2;
+  float2 m = make_float2(0.f, 0.f);
+  if (lane < f.splits) m = __ldcg(reinterpret_cast<const float2 *>(st + ((int64_t)lane * 64 + b) * 2));
+  return m;
 }
+__device__ __forceinline__ void ln_fold_moments_finish(const LnFoldStats &f, float2 m, float &mean, float &rstd) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m.x += __shfl_xor_sync(0xffffffffu, m.x, o);
+    m.y += __shfl_xor_sync(0xffffffffu, m.y, o);
+  }
+  mean = m.x / (float)f.d;
+  rstd = rsqrtf(fmaxf(m.y / (float)f.d - mean * mean, 0.f) + f.eps);
+}
+__device__ __forceinline__ void ln_fold_moments(const LnFoldStats &f, int b, int which, float &mean, float &rstd) {
+  ln_fold_moments_finish(f, ln_fold_moments_load(f, b, which), mean, rstd);
+}
+struct XRelu {           // finished rows of the folded projection: out16[b, n] = bf16(relu(LayerNorm(x) W^T + b))
+  const float *c, *dvec; // vb_ln_fold vectors
+  float eps;
+  bf16 *out16;
+  int64_t ld_out;
+};
 int launch_gemm_decode_x(const float *x, int B, int64_t ldx, const bf16 *Wf, int N, int K, int force_splits,
                          float *partials, size_t partial_bytes, float *stats, int *out_splits, int *out_ldp,
-                         const KvPrefetch *pf, bool pdl, cudaStream_t s);
+                         int *out_copies, const KvPrefetch *pf, bool pdl, cudaStream_t s, const XRelu *relu = nullptr);
 int launch_ln_fold(const bf16 *W, int N, int K, const float *gamma, const float *beta, const float *bias, bf16 *wf,
                    float *c, float *dvec, cudaStream_t s);
 

@@ -62,7 +62,7 @@ ar_sample_kernel(float *__restrict__ logits, int64_t ld_logits, const float *__r
   // final LayerNorm folded into ar_predict_layer (gemm_decode_x_kernel): logit = rstd (acc - mean c[i]) + (beta W^T)[i]
   float f_mean = 0.f, f_rstd = 1.f;
   const bool folded = fold.stats != nullptr && partials != nullptr;
-  if (folded) ln_fold_moments(fold, b, f_mean, f_rstd);
+  if (folded) ln_fold_moments(fold, b, b, f_mean, f_rstd);
   if (partials && n_vocab <= 5 * 256 && splits <= 8) {
     // head projection split-K partials, summed in fixed order; all loads of the row issued at once
     float v[5][8];
@@ -150,6 +150,8 @@ int launch_ar_sample(float *logits, int64_t ld_logits, const float *partials, in
                      cudaStream_t s, const LnFoldStats *fold) {
   LnFoldStats f{};
   if (fold) f = *fold;
+  static PerDeviceOnce once;
+  if (once.first()) prefer_chain_carveout(ar_sample_kernel);
   const float *fold_d = fold ? head->fold.dvec : nullptr;
   VB_CUDA(launch_kernel(ar_sample_kernel, dim3(st->B), dim3(256), 0, s, pdl, logits, ld_logits, partials, splits, ldp,
                         head->n_vocab, head->eos_id, head->audio_emb, head->alpha, head->pe, head->pe_rows,
