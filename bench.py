@@ -500,7 +500,7 @@ def main():
     ach = ar_bytes / ar_step_s / 1e9
     # DRAM bytes of one decode step from the committed ncu capture (tools/ar_step_traffic.py), if there is one
     traffic, traffic_src = None, None
-    for tp in ("round2_ar_step_traffic.json", "round1_ar_step_traffic.json"):
+    for tp in ("round2_ar_step_traffic_fold.json", "round2_ar_step_traffic.json", "round1_ar_step_traffic.json"):
         tp = os.path.join(ROOT, "profiles", tp)
         if B == 64 and esize == 2 and os.path.exists(tp):
             with open(tp) as f:
@@ -526,6 +526,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": re["ms"] / a.steps},
         "roofline": {"kernel": "AR decode step (CUDA graph of the PDL-chained projection / KV-cache attention kernels)",
+                     "chain": ("LayerNorms folded into the projections, 6 launches per layer"
+                               if getattr(eng, "ar_head_fold", None) is not None else "8 launches per layer"),
                      "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": ach / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                      "peak_source": pk["source"],

@@ -86,6 +86,31 @@ __device__ __forceinline__ uint4 ldg_stream16(const void *p) {
                : "l"(p));
   return r;
 }
+// the same with an L2 eviction policy (createpolicy): the KV-cache rows of a decode step are read exactly once, marking
+// them evict-first keeps them from pushing the lines that were prefetched for LATER use (the rest of this launch's
+// streams, the next projections' weights) out of L2
+__device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
+  uint64_t pol;
+  if (evict_first)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ldg_stream16_hint(const void *p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+// L2 prefetch; keep = 1 marks the line evict-last (it is going to be read once, later)
+__device__ __forceinline__ void prefetch_l2(const void *p, int keep) {
+  if (keep)
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+  else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 template <typename T> __device__ __forceinline__ Vec16<T> load_stream(const T *p);
 template <> __device__ __forceinline__ Vec16<float> load_stream<float>(const float *p) {
   Vec16<float> v;
