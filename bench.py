@@ -500,7 +500,7 @@ def main():
     ach = ar_bytes / ar_step_s / 1e9
     # DRAM bytes of one decode step from the committed ncu capture (tools/ar_step_traffic.py), if there is one
     traffic, traffic_src = None, None
-    for tp in ("round2_ar_step_traffic_fold.json", "round2_ar_step_traffic.json", "round1_ar_step_traffic.json"):
+    for tp in ("round2b_ar_step_traffic_fold.json", "round2_ar_step_traffic.json", "round1_ar_step_traffic.json"):
         tp = os.path.join(ROOT, "profiles", tp)
         if B == 64 and esize == 2 and os.path.exists(tp):
             with open(tp) as f:

@@ -538,7 +538,10 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
     // on one box, AR phase per step: 0 -> 589.6, 1 -> 593.0, 3 -> 600.2 us (and 7 worse over the long contexts of a
     // full decode); a policy operand on every K / V load costs more than the protected prefetch lines return
     const int l2_hints = tune("VB_L2_HINTS", 0);
-    const int pf_env = tune("VB_KV_PREFETCH_PCT", 40);
+    // (40 % for the 8-launch chain; the folded chain leaves the projections less time ahead of the attention launch:
+    //  30-35 % measured 1-2 % better than 40 %)
+    const bool fold_on = dec->fold_qkv && dec->fold_ffn1 && head->fold.wf && tune("VB_DECODE_FOLD", 1) != 0;
+    const int pf_env = tune("VB_KV_PREFETCH_PCT", fold_on ? 35 : 40);
     const int pf_pct = B >= 16 ? pf_env : 0;
     const int qkv_env = tune("VB_SPLITS_QKV", 0);
     const int out_splits = tune("VB_SPLITS_OUT", 0);   // 0 = fill the SMs
@@ -566,8 +569,7 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
       pf.keep = (l2_hints & 2) ? 1 : 0;
       return pf;
     };
-    const bool fold = dec->fold_qkv && dec->fold_ffn1 && head->fold.wf && tune("VB_DECODE_FOLD", 1) != 0;
-    if (fold) {
+    if (fold_on) {
       // Folded chain, 6 launches per layer: the residual stream x is assembled in place by the split-K projections that
       // produce it (red.global.add of every split's tile), the projections that consume it read the fp32 rows and carry
       // the LayerNorm in their weights (vb_ln_fold), the rows' moments travel with the partial sums:
