@@ -319,7 +319,10 @@ int vb_ar_head_step(vb_decoder_t dec, const vb_ar_head *head, const float *h, vb
 
 /* one decode step for all B rows: 12 x (LN -> QKV -> KV append -> single-query attention over
  * the cache -> out-proj -> LN -> FFN), then vb_ar_head_step.  Safe to capture in a CUDA graph
- * (no host reads; launch geometry depends only on B and cache_cap). */
+ * (no host reads; launch geometry depends only on B and cache_cap).  bf16 decoders with
+ * vb_decoder_set_decode_fold + head->fold run the LayerNorm-folded chain (6 launches per layer; the
+ * residual stream is assembled by bulk reductions whose order over the split-K slabs is not fixed:
+ * last-bit differences between runs, VB_DECODE_FOLD=0 selects the fixed-order 8-launch chain). */
 int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_state *st, void *workspace,
                       size_t workspace_bytes, vb_stream_t stream);
 
