@@ -533,11 +533,6 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
     // enough to fill the SMs is not the optimum for the projections whose partial sums a reduce kernel has to add
     // up again (FFN2: 9 splits beat 18, QKV: 5 beat 6, FFN1: 2 beat 4); 40 % of the KV streams prefetched into L2
     // beat 20 / 60 %.
-    // L2 eviction hints (experiment knob, default off): 1 = the attention's K / V loads carry the evict-first policy,
-    // 2 = the KV prefetch lines are marked evict-last, 4 = the weight prefetch lines are marked evict-last.  Measured
-    // on one box, AR phase per step: 0 -> 589.6, 1 -> 593.0, 3 -> 600.2 us (and 7 worse over the long contexts of a
-    // full decode); a policy operand on every K / V load costs more than the protected prefetch lines return
-    const int l2_hints = tune("VB_L2_HINTS", 0);
     // (40 % for the 8-launch chain; the folded chain leaves the projections less time ahead of the attention launch:
     //  30-35 % measured 1-2 % better than 40 %)
     const bool fold_on = dec->fold_qkv && dec->fold_ffn1 && head->fold.wf && tune("VB_DECODE_FOLD", 1) != 0;
@@ -566,7 +561,6 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
       pf.B = B; pf.H = D.n_head; pf.cap = st->cache_cap; pf.row_bytes = (int)(hd * ts);
       pf.text_len = st->text_len; pf.prompt_len = st->prompt_len; pf.n_gen = st->n_gen;
       pf.lo_pct = pf_pct * quarter / 4; pf.hi_pct = pf_pct * (quarter + 1) / 4;
-      pf.keep = (l2_hints & 2) ? 1 : 0;
       return pf;
     };
     if (fold_on) {
@@ -577,13 +571,6 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
       const int qkv_f = qkv_env > 0 ? qkv_env : std::max(1, std::min(5, d / 128));
       const int ffn1_f = ffn1_env > 0 ? ffn1_env : std::max(1, std::min(4, d / 128));
       const int out_f = out_splits > 0 ? out_splits : 8;
-      // (linear1 + ReLU in one launch -- the splits of a tile as a thread-block cluster reducing over DSMEM -- measured
-      //  slower: 9.5 + 8.2 us for FFN1 + FFN2 against 5.0 + 4.9 + 6.6 us with the separate reduce launch)
-      const bool relu_in_cluster = tune("VB_FFN1_CLUSTER", 0) != 0;
-      const bool dbg_nomom = tune("VB_FOLD_DEBUG_NOMOM", 0) != 0;   // timing experiment only (wrong numerics)
-      // (weights of the following projections prefetched into L2 by the attention CTAs: measured neutral -- FFN2's block
-      //  time 6.8 vs 7.3 us, AR phase 604.6 vs 607.5 us / step -- off by default)
-      const bool w_prefetch = tune("VB_W_PREFETCH", 0) != 0;
       for (int l = 0; l < D.n_layer; ++l) {
         const vb_layer_params &L = dec->layers[l];
         const vb_ln_fold &Fq = dec->fold_qkv[l], &Ff = dec->fold_ffn1[l];
@@ -594,36 +581,17 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
         int s1 = 1, ldp1 = 0, cp1 = 1;
         VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)Fq.wf, 3 * d, d, qkv_f, P, w.gemm_ws_bytes, w.stats, &s1, &ldp1,
                                     &cp1, &pf_qkv, pdl, s));
-        const LnFoldStats fq{w.stats, Fq.c, dbg_nomom ? 0 : s1, d, 1e-5f, cp1};
-        WPrefetch wp{};
-        wp.keep = (l2_hints & 4) ? 1 : 0;
-        wp.stream_evict_first = (l2_hints & 1) ? 1 : 0;
-        if (w_prefetch) {
-          wp.ptr[0] = L.out_proj_w; wp.bytes[0] = (unsigned long long)d * d * 2;
-          wp.ptr[1] = Ff.wf;        wp.bytes[1] = (unsigned long long)dff * d * 2;
-          wp.ptr[2] = L.lin2_w;     wp.bytes[2] = (unsigned long long)d * dff * 2;
-          if (l + 1 < D.n_layer) {
-            wp.ptr[3] = dec->fold_qkv[l + 1].wf; wp.bytes[3] = (unsigned long long)3 * d * d * 2;
-          } else {
-            wp.ptr[3] = head->fold.wf; wp.bytes[3] = (unsigned long long)head->n_vocab * d * 2;
-          }
-        }
+        const LnFoldStats fq{w.stats, Fq.c, s1, d, 1e-5f, cp1};
         VB_TRY(launch_attn_decode(w.q, P, s1, ldp1, Fq.dvec, B, D.n_head, hd, kc, vc, dt, st->cache_seq_stride,
                                   st->cache_cap, st->text_len, st->prompt_len, st->n_gen, st->finished, w.att, w.att16,
-                                  w.attn_ws, pdl, s, &fq, &wp));
+                                  w.attn_ws, pdl, s, &fq));
         VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)L.out_proj_w, d, d, out_f, L.out_proj_b, DG_RESIDUAL, x,
                                   nullptr, d, nullptr, nullptr, 0, nullptr, nullptr, &pf_out, pdl, s, true));
-        if (relu_in_cluster) {   // linear1 + ReLU in one launch: the splits of a tile reduce over DSMEM
-          const XRelu xr{Ff.c, Ff.dvec, 1e-5f, w.hb16, dff};
-          VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)Ff.wf, dff, d, ffn1_f, nullptr, 0, nullptr, nullptr, nullptr,
-                                      nullptr, &pf_f1, pdl, s, &xr));
-        } else {
-          int sf = 1, ldpf = 0, cpf = 1;
-          VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)Ff.wf, dff, d, ffn1_f, P, w.gemm_ws_bytes, w.stats, &sf,
-                                      &ldpf, &cpf, &pf_f1, pdl, s));
-          const LnFoldStats ff{w.stats, Ff.c, dbg_nomom ? 0 : sf, d, 1e-5f, cpf};
-          VB_TRY(launch_relu_reduce(P, sf, ldpf, Ff.dvec, B, dff, w.hb16, dff, pdl, s, &ff));
-        }
+        int sf = 1, ldpf = 0, cpf = 1;
+        VB_TRY(launch_gemm_decode_x(x, B, d, (const bf16 *)Ff.wf, dff, d, ffn1_f, P, w.gemm_ws_bytes, w.stats, &sf, &ldpf,
+                                    &cpf, &pf_f1, pdl, s));
+        const LnFoldStats ff{w.stats, Ff.c, sf, d, 1e-5f, cpf};
+        VB_TRY(launch_relu_reduce(P, sf, ldpf, Ff.dvec, B, dff, w.hb16, dff, pdl, s, &ff));
         VB_TRY(launch_gemm_decode(w.hb16, B, dff, (const bf16 *)L.lin2_w, d, dff, ffn2_fold, L.lin2_b, DG_RESIDUAL, x,
                                   nullptr, d, nullptr, nullptr, 0, nullptr, nullptr, &pf_f2, pdl, s, true));
       }
@@ -642,19 +610,9 @@ VB_API int vb_ar_decode_step(vb_decoder_t dec, const vb_ar_head *head, vb_ar_sta
       int s1 = 1, ldp1 = 0;
       VB_TRY(launch_gemm_decode(w.xn16, B, d, (const bf16 *)L.in_proj_w, 3 * d, d, qkv_splits, L.in_proj_b, DG_QKV, nullptr,
                                 nullptr, d, &sc, P, w.gemm_ws_bytes, &s1, &ldp1, &pf_qkv, pdl, s));
-      WPrefetch wp{};
-      wp.keep = (l2_hints & 4) ? 1 : 0;
-      wp.stream_evict_first = (l2_hints & 1) ? 1 : 0;
-      if (tune("VB_W_PREFETCH", 0) != 0) {
-        wp.ptr[0] = L.out_proj_w; wp.bytes[0] = (unsigned long long)d * d * 2;
-        wp.ptr[1] = L.lin1_w;     wp.bytes[1] = (unsigned long long)dff * d * 2;
-        wp.ptr[2] = L.lin2_w;     wp.bytes[2] = (unsigned long long)d * dff * 2;
-        wp.ptr[3] = l + 1 < D.n_layer ? dec->layers[l + 1].in_proj_w : head->predict_w;
-        wp.bytes[3] = l + 1 < D.n_layer ? (unsigned long long)3 * d * d * 2 : (unsigned long long)head->n_vocab * d * 2;
-      }
       VB_TRY(launch_attn_decode(w.q, s1 > 1 ? P : nullptr, s1, ldp1, L.in_proj_b, B, D.n_head, hd, kc, vc, dt,
                                 st->cache_seq_stride, st->cache_cap, st->text_len, st->prompt_len, st->n_gen, st->finished,
-                                w.att, w.att16, w.attn_ws, pdl, s, nullptr, &wp));
+                                w.att, w.att16, w.attn_ws, pdl, s));
       int s2 = 1, ldp2 = 0;
       VB_TRY(launch_gemm_decode(w.att16, B, d, (const bf16 *)L.out_proj_w, d, d, out_splits, L.out_proj_b, DG_RESIDUAL, x,
                                 nullptr, d, nullptr, P, w.gemm_ws_bytes, &s2, &ldp2, &pf_out, pdl, s));

@@ -435,14 +435,14 @@ attn_decode_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, T *_
 // of K rows fetched ahead of the q/k/v prologue (and, with the fused QKV prologue, ahead of the dependency wait)
 // and the first batch of V rows fetched ahead of the block softmax: all CTAs of the single wave run their phases
 // in lock step, so without this the HBM pipe idles through every prologue / softmax / epilogue of the launch.
-template <int U, bool kEvictFirst>
+template <int U>
 __global__ void __launch_bounds__(128, 7)
 attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_head, bf16 *__restrict__ kcache,
                    bf16 *__restrict__ vcache, int64_t cache_seq_stride, int cache_cap,
                    const int32_t *__restrict__ text_len, const int32_t *__restrict__ prompt_len,
                    const int32_t *__restrict__ n_gen, const int32_t *__restrict__ finished,
                    float *__restrict__ out, bf16 *__restrict__ out16,
-                   float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit, WPrefetch wp) {
+                   float *__restrict__ part_o, float *__restrict__ part_ml, int nsplit) {
   // score buffer of the chunk: dynamic shared memory sized by the launch (cache_cap / nsplit keys), so that the
   // kernel's footprint -- and with it the shared-memory carve-out the driver picks, i.e. how much L1 is left to land
   // the ~110 KB of K / V loads an SM keeps in flight -- follows the actual context instead of the 4096-key maximum
@@ -469,10 +469,6 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
   // the wait and the batch re-requested should it have moved (it cannot when steps are separate graph launches).
   int kv_len, pos, c0, c1, n;
   uint4 kraw[U];
-  // K / V rows are read once: with kEvictFirst they carry the L2 evict-first policy, so the stream does not push the
-  // lines prefetched for later use out of L2 (the plain form is kept: a policy operand on every load is not free)
-  const uint64_t pol = kEvictFirst ? l2_policy(true) : 0ull;
-  auto ldkv = [&](const void *p) { return kEvictFirst ? ldg_stream16_hint(p, pol) : ldg_stream16(p); };
   auto setup = [&](int n_generated) {
     kv_len = max(1, min(text_len[b] + prompt_len[b] + n_generated, cache_cap));
     pos = kv_len - 1;  // cache row of the current token
@@ -483,16 +479,13 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
     if (n > 0) {
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        kraw[u] = ldkv(kb + (int64_t)(c0 + min(u * 16 + warp * 4 + g, n - 1)) * HD + j8);
+        kraw[u] = ldg_stream16(kb + (int64_t)(c0 + min(u * 16 + warp * 4 + g, n - 1)) * HD + j8);
     }
   };
   // (only with the fused QKV prologue: there the current token's row is served from shared memory; without it the
   // row was written to the cache by the kernel this launch depends on and nothing may be read ahead of the wait)
   const int n_gen_early = has_new ? n_gen[b] : -1;
   if (has_new) setup(n_gen_early);
-  // weights of the projections that follow this launch -> L2 (see WPrefetch), behind this CTA's first K rows
-  weight_prefetch(wp, ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 128u + tid,
-                  gridDim.x * gridDim.y * gridDim.z * 128u);
   float qbias[3] = {0.f, 0.f, 0.f}, qc[3] = {0.f, 0.f, 0.f};
   if (tid < HD && has_new) {
 #pragma unroll
@@ -567,7 +560,7 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
     if (base > 0) {
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        kraw[u] = ldkv(kb + (int64_t)(c0 + min(base + u * 16 + warp * 4 + g, n - 1)) * HD + j8);
+        kraw[u] = ldg_stream16(kb + (int64_t)(c0 + min(base + u * 16 + warp * 4 + g, n - 1)) * HD + j8);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -593,7 +586,7 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
   uint4 vraw[U];
   if (n > 0) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) vraw[u] = ldkv(vb_ + (int64_t)(c0 + min(u * 16 + jl, n - 1)) * HD + eg);
+    for (int u = 0; u < U; ++u) vraw[u] = ldg_stream16(vb_ + (int64_t)(c0 + min(u * 16 + jl, n - 1)) * HD + eg);
   }
   if (new_here && warp == 0) {  // score of the current token from the shared-memory key (never from the cache)
     float dot = 0.f;
@@ -632,7 +625,7 @@ attn_decode_2phase_pf_kernel(const float *__restrict__ q, QkvPartials qp, int n_
     if (base > 0) {
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        vraw[u] = ldkv(vb_ + (int64_t)(c0 + min(base + u * 16 + jl, n - 1)) * HD + eg);
+        vraw[u] = ldg_stream16(vb_ + (int64_t)(c0 + min(base + u * 16 + jl, n - 1)) * HD + eg);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -716,7 +709,7 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
                        int B, int n_head, int head_dim, void *kcache, void *vcache, int dtype,
                        int64_t cache_seq_stride, int cache_cap, const int32_t *text_len, const int32_t *prompt_len,
                        const int32_t *n_gen, const int32_t *finished, float *out, void *out16, void *workspace,
-                       bool pdl, cudaStream_t s, const LnFoldStats *fold, const WPrefetch *wp) {
+                       bool pdl, cudaStream_t s, const LnFoldStats *fold) {
   VB_CHECK_ARG(head_dim == HD, "attn_decode: head_dim=%d, only 64 is built", head_dim);
   const int ns = decode_nsplit(B, n_head, cache_cap);
   VB_CHECK_ARG((cache_cap + ns - 1) / ns + 16 <= kDecMaxChunk, "attn_decode: cache_cap %d too large", cache_cap);
@@ -724,14 +717,6 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
   float *part_ml = part_o + (size_t)B * n_head * ns * HD;
   QkvPartials qp{qkv_part, qkv_bias, qkv_splits, qkv_ldp, LnFoldStats{}};
   if (fold) qp.fold = *fold;
-  static PerDeviceOnce once;
-  if (once.first()) {
-    prefer_chain_carveout(attn_decode_kernel<float>);
-    prefer_chain_carveout(attn_decode_kernel<bf16>);
-    prefer_chain_carveout(attn_decode_2phase_pf_kernel<8, true>);
-    prefer_chain_carveout(attn_decode_2phase_pf_kernel<8, false>);
-    prefer_chain_carveout(attn_decode_combine_kernel);
-  }
   dim3 grid(n_head, B, ns);
   if (dtype == VB_F32 || getenv("VB_ATTN_DECODE_1PASS") != nullptr) {  // fp32 parity path / single-pass variant
     if (dtype == VB_F32)
@@ -760,22 +745,13 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
     const int carve = tune("VB_ATTN_CARVEOUT", 72);
     if (carve_set[dev & 63] != carve) {
       const int want = carve >= 0 ? carve : (int)cudaSharedmemCarveoutDefault;
-      if (carve >= 0 || carve_set[dev & 63] != -2) {
-        VB_CUDA(cudaFuncSetAttribute(attn_decode_2phase_pf_kernel<8, true>, cudaFuncAttributePreferredSharedMemoryCarveout, want));
-        VB_CUDA(cudaFuncSetAttribute(attn_decode_2phase_pf_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, want));
-      }
+      if (carve >= 0 || carve_set[dev & 63] != -2)
+        VB_CUDA(cudaFuncSetAttribute(attn_decode_2phase_pf_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, want));
       carve_set[dev & 63] = carve;
     }
-    WPrefetch wp0{};
-    if (wp) wp0 = *wp;
-    if (wp0.stream_evict_first)
-      VB_CUDA(launch_kernel(attn_decode_2phase_pf_kernel<8, true>, grid, dim3(128), sc_bytes, s, pdl, q, qp, n_head,
-                            (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen,
-                            finished, out, (bf16 *)out16, part_o, part_ml, ns, wp0));
-    else
-      VB_CUDA(launch_kernel(attn_decode_2phase_pf_kernel<8, false>, grid, dim3(128), sc_bytes, s, pdl, q, qp, n_head,
-                            (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen,
-                            finished, out, (bf16 *)out16, part_o, part_ml, ns, wp0));
+    VB_CUDA(launch_kernel(attn_decode_2phase_pf_kernel<8>, grid, dim3(128), sc_bytes, s, pdl, q, qp, n_head,
+                          (bf16 *)kcache, (bf16 *)vcache, cache_seq_stride, cache_cap, text_len, prompt_len, n_gen,
+                          finished, out, (bf16 *)out16, part_o, part_ml, ns));
   }
   count_launch();
   if (ns > 1) {

@@ -86,31 +86,6 @@ __device__ __forceinline__ uint4 ldg_stream16(const void *p) {
                : "l"(p));
   return r;
 }
-// the same with an L2 eviction policy (createpolicy): the KV-cache rows of a decode step are read exactly once, marking
-// them evict-first keeps them from pushing the lines that were prefetched for LATER use (the rest of this launch's
-// streams, the next projections' weights) out of L2
-__device__ __forceinline__ uint64_t l2_policy(bool evict_first) {
-  uint64_t pol;
-  if (evict_first)
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  else
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ uint4 ldg_stream16_hint(const void *p, uint64_t pol) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p), "l"(pol));
-  return r;
-}
-// L2 prefetch; keep = 1 marks the line evict-last (it is going to be read once, later)
-__device__ __forceinline__ void prefetch_l2(const void *p, int keep) {
-  if (keep)
-    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
-  else
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 template <typename T> __device__ __forceinline__ Vec16<T> load_stream(const T *p);
 template <> __device__ __forceinline__ Vec16<float> load_stream<float>(const float *p) {
   Vec16<float> v;
@@ -247,15 +222,6 @@ struct PerDeviceOnce {
     return true;
   }
 };
-
-// Experiment knob: VB_CHAIN_CARVEOUT = percentage makes every kernel of the PDL-chained decode step prefer the same
-// shared-memory / L1 partition of the SM.  Measured (profiles/round2_summary.md): forcing the largest carve-out slows
-// the KV-cache attention from 25.7 to 32.1 us per launch -- its ~110 KB of loads in flight per SM need the L1 lines --
-// so the default (-1) leaves the driver's per-kernel choice (164 KB for the projections and the attention alike).
-template <typename K> inline void prefer_chain_carveout(K kern) {
-  const int pct = tune("VB_CHAIN_CARVEOUT", -1);
-  if (pct >= 0) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-}
 
 // ---- device timeline (profiling builds only: -DVB_TRACE, libvalle_b200_trace.so) ----------------
 // Thread 0 of block (0,0,0) of a traced kernel appends (globaltimer << 8 | id) to a ring bound with

@@ -153,8 +153,6 @@ int launch_relu_reduce(const float *partials, int splits, int ldp, const float *
   VB_CHECK_ARG(N % 4 == 0 && ldo % 4 == 0, "relu_reduce: N %% 4 != 0");
   LnFoldStats f{};
   if (fold) f = *fold;
-  static PerDeviceOnce once;
-  if (once.first()) prefer_chain_carveout(relu_reduce_kernel);
   VB_CUDA(launch_kernel(relu_reduce_kernel, dim3((N / 4 + 255) / 256, B), dim3(256), 0, s, pdl, partials, splits, ldp,
                         bias, N, out16, ldo, f));
   count_launch();
@@ -167,12 +165,6 @@ int launch_ln_reduce(float *x, int64_t ldx, int B, int d, const float *partials,
   VB_CHECK_ARG(d % 4 == 0 && ldx % 4 == 0 && d <= 4096, "ln_reduce: bad d=%d", d);
   const dim3 grid(B), block(256);
   const int slabs = (d + 1023) / 1024;
-  static PerDeviceOnce once;
-  if (once.first()) {
-    prefer_chain_carveout(ln_reduce_kernel<1>);
-    prefer_chain_carveout(ln_reduce_kernel<2>);
-    prefer_chain_carveout(ln_reduce_kernel<4>);
-  }
   if (slabs <= 1)
     VB_CUDA(launch_kernel(ln_reduce_kernel<1>, grid, block, 0, s, pdl, x, ldx, B, d, partials, splits, ldp, bias,
                           gamma, beta, eps, out16));

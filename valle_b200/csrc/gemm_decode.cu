@@ -42,7 +42,6 @@ struct Epi {
   int mode;  // DG_* below
   int red;   // DG_RESIDUAL with split-K, no partials: 1 = every split adds its tile into out_f32 by a TMA bulk reduction
              // (order of the splits not fixed), 2 = the splits of a tile are a cluster and reduce over DSMEM in fixed order
-  int red_wait_full;
   int N, B;  // valid output features / rows
   const float *bias;
   float *out_f32;      // [B, ld_out] (RESIDUAL: in/out; F32: out; QKV: q)
@@ -212,10 +211,8 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       if (q == 0 && lane == 0) {
         tma_reduce_add_2d(&tmap_red, sv, tile * TM, 0);
         tma_store_commit();
-        if (epi.red_wait_full)
-          asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // performed before this CTA retires
-        else
-          tma_store_wait_read<0>();  // shared memory read; the reduction itself completes with the grid
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // performed before this CTA retires (waiting only for
+                                                                  // the shared-memory read measured the same)
       }
     } else if (epi.red == 2) {
       // deterministic variant: the CTAs of a tile (its `splits` splits) form a thread-block cluster; every CTA parks
@@ -285,34 +282,21 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 constexpr int kStagesX = 4;   // the chain's split counts keep a CTA at <= 4 k-blocks: the ring never wraps
 constexpr int kXfBytes = TN * BK * 4;  // 16 KB fp32 box
 constexpr int kStageBytesX = kWBytes + kXBytes + kXfBytes;  // 40 KB
-constexpr int kSmemBytesX = kStagesX * kStageBytesX + 1024 + 1024;  // + alignment slack, barriers (256 B), row moments (512 B)
+constexpr int kSmemBytesX = kStagesX * kStageBytesX + 1024 + 512;   // + alignment slack, barriers
 
-// mode 1 (the `splits` CTAs of a tile are one thread-block cluster): the partial tiles and the rows' moments are added up
-// over DSMEM in fixed order, the folded LayerNorm and ReLU applied, and the bf16 hidden rows written -- linear1 + ReLU
-// of the FFN (transformer.py:332-334) without the separate reduce launch
-struct XEpi {
-  int mode;            // 0: fp32 partials + moments to global memory, 1: cluster reduce -> LayerNorm fold -> ReLU -> bf16
-  int N, B, d;         // valid features / rows, LayerNorm width
-  float eps;
-  const float *c, *dvec;
-  bf16 *out16;
-  int64_t ld_out;
-};
 constexpr int kThreadsX = 448;  // warp 0 TMA, 1 MMA, 2..9 converters (4..7 also the epilogue), 10..13 KV prefetch
 
 // (register cap of two CTAs per SM: 72 registers, no spills -- with the 4-stage ring that leaves room for three CTAs of
 //  the attention launch that follows to become resident, and fetch their first K rows, while this kernel still runs)
 __global__ void __launch_bounds__(kThreadsX, 2)
 gemm_decode_x_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_xf,
-                     int num_kb, float *__restrict__ partials, int ldp, float *__restrict__ stats, KvPrefetch pf,
-                     XEpi xe) {
+                     int num_kb, float *__restrict__ partials, int ldp, float *__restrict__ stats, KvPrefetch pf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t *bars = reinterpret_cast<uint64_t *>(tiles + kStagesX * kStageBytesX);
   uint64_t *wfull = bars, *xfull = bars + kStagesX, *bfull = bars + 2 * kStagesX, *empty_bar = bars + 3 * kStagesX,
            *tmem_full = bars + 4 * kStagesX;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
-  float2 *mom = reinterpret_cast<float2 *>(reinterpret_cast<uint8_t *>(bars) + 256);  // [TN] (sum x, sum x^2), mode 1
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, split = blockIdx.y, splits = gridDim.y;
@@ -431,7 +415,7 @@ gemm_decode_x_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         phase ^= 1;
       }
     }
-    if (xe.mode == 1 || (tile < kLnFoldMaxCopies && stats != nullptr)) {  // moments of this split's k-range
+    if (tile < kLnFoldMaxCopies && stats != nullptr) {  // moments of this split's k-range: stats[tile][split][row][2]
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
 #pragma unroll
@@ -441,20 +425,15 @@ gemm_decode_x_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
         }
         if (f == 0) {
           const int r = cw * 8 + it * 2 + rsub;
-          if (xe.mode == 1)
-            mom[r] = make_float2(s1[it], s2[it]);   // read by the cluster over DSMEM
-          else                                        // stats[tile][split][row][2]
-            *reinterpret_cast<float2 *>(stats + (((int64_t)tile * splits + split) * TN + r) * 2) =
-                make_float2(s1[it], s2[it]);
+          *reinterpret_cast<float2 *>(stats + (((int64_t)tile * splits + split) * TN + r) * 2) =
+              make_float2(s1[it], s2[it]);
         }
       }
     }
     if (warp >= 4 && warp < 8) {  // ---- epilogue: fp32 partial tile of this split, 32 rows at a time ----
       const int q = warp & 3;
-      const int nl = q * 32 + lane;
-      const int n = tile * TM + nl;
+      const int n = tile * TM + q * 32 + lane;
       float *mine = partials + (int64_t)split * TN * ldp + n;
-      float *sv = reinterpret_cast<float *>(tiles);  // mode 1: [TN][TM] in the (by then idle) pipeline memory
       if (nkb > 0) {
         mbar_wait(tmem_full, 0);
         tcgen05_fence_after();
@@ -468,13 +447,8 @@ gemm_decode_x_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = 0u;
         }
-        if (xe.mode == 1) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) sv[(half * 32 + i) * TM + nl] = __uint_as_float(r[i]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mine[(int64_t)(half * 32 + i) * ldp] = __uint_as_float(r[i]);
-        }
+        for (int i = 0; i < 32; ++i) mine[(int64_t)(half * 32 + i) * ldp] = __uint_as_float(r[i]);
       }
     }
   } else {
@@ -483,67 +457,6 @@ gemm_decode_x_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_co
     pdl_wait();
   }
   __syncwarp();
-  if (xe.mode == 1) {
-    // every CTA of the cluster has parked its tile and its moments (all MMAs of the cluster have retired)
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    uint32_t crank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-    const int R = (TN + splits - 1) / splits;            // rows of this CTA's slice
-    const int b_lo = (int)crank * R;
-    float2 *mr = reinterpret_cast<float2 *>(tiles + TN * TM * 4);   // [R] (mean, rstd) of the slice's rows
-    if (warp == 2) {
-      for (int rr = lane; rr < R && b_lo + rr < TN; rr += 32) {
-        const uint32_t a0 = smem_u32(mom + b_lo + rr);
-        float s1 = 0.f, s2 = 0.f;
-        float2 t[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          t[j] = make_float2(0.f, 0.f);
-          if (j < splits) {
-            uint32_t ra;
-            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a0), "r"(j));
-            asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(t[j].x), "=f"(t[j].y) : "r"(ra) : "memory");
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s1 += t[j].x;
-          s2 += t[j].y;
-        }
-        const float mean = s1 / (float)xe.d;
-        mr[rr] = make_float2(mean, rsqrtf(fmaxf(s2 / (float)xe.d - mean * mean, 0.f) + xe.eps));
-      }
-      asm volatile("bar.sync 2, 160;" ::: "memory");
-    } else if (warp >= 4 && warp < 8) {
-      const int nl = (warp & 3) * 32 + lane, n = tile * TM + nl;
-      const float cn = n < xe.N ? xe.c[n] : 0.f, dn = n < xe.N ? xe.dvec[n] : 0.f;
-      uint32_t ra[8];
-      const uint32_t sv_addr = smem_u32(tiles) + (uint32_t)nl * 4u;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra[j]) : "r"(sv_addr), "r"(min(j, splits - 1)));
-      asm volatile("bar.sync 2, 160;" ::: "memory");
-      const int b_hi = min(min(b_lo + R, TN), xe.B);
-#pragma unroll 2
-      for (int b = b_lo; b < b_hi; ++b) {
-        float t[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          t[j] = 0.f;
-          if (j < splits)
-            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(t[j]) : "r"(ra[j] + (uint32_t)(b * TM * 4)) : "memory");
-        }
-        float acc = t[0];
-#pragma unroll
-        for (int j = 1; j < 8; ++j) acc += t[j];   // fixed order 0..S-1
-        const float2 m = mr[b - b_lo];
-        const float h = fmaxf(m.y * (acc - m.x * cn) + dn, 0.f);
-        if (n < xe.N) xe.out16[(int64_t)b * xe.ld_out + n] = __float2bfloat16_rn(h);
-      }
-    }
-    // nobody leaves while its tile may still be read
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  }
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -597,7 +510,6 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
   dg::Epi e{};
   e.mode = mode; e.N = N; e.B = B; e.bias = bias;
   e.red = (red_add && splits > 1) ? (tune("VB_RED_MODE", 1) == 2 && splits <= 8 ? 2 : 1) : 0;
-  e.red_wait_full = tune("VB_RED_WAIT_FULL", 1);
   e.out_f32 = out_f32; e.out_bf16 = out_bf16; e.ld_out = ld_out;
   if (mode == DG_QKV && splits == 1) {
     VB_CHECK_ARG(qkv != nullptr, "gemm_decode: qkv scatter parameters missing");
@@ -612,7 +524,6 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
   if (once.first()) {
     VB_CUDA(cudaFuncSetAttribute(dg::gemm_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  dg::kSmemBytes));
-    prefer_chain_carveout(dg::gemm_decode_kernel);
   }
   KvPrefetch pf0{};
   if (pf) pf0 = *pf;
@@ -623,21 +534,20 @@ int launch_gemm_decode(const bf16 *act, int B, int64_t ld_act, const bf16 *W, in
 }
 
 // projection of the fp32 rows x[B, K] by LayerNorm-folded weights: fp32 partial tiles + the rows' moments per split
-// (relu16 == NULL), or -- `splits` <= 8 CTAs of a tile as one cluster -- the finished bf16 rows relu(LayerNorm(x) W^T + b)
+// (linear1 + ReLU finished inside this launch -- the splits of a tile as a thread-block cluster reducing over DSMEM --
+//  was built and measured slower: 9.5 + 8.2 us for FFN1 + FFN2 against 5.0 + 2.7 + 7.4 us with relu_reduce_kernel)
 int launch_gemm_decode_x(const float *x, int B, int64_t ldx, const bf16 *Wf, int N, int K, int force_splits,
                          float *partials, size_t partial_bytes, float *stats, int *out_splits, int *out_ldp,
-                         int *out_copies, const KvPrefetch *pf, bool pdl, cudaStream_t s, const XRelu *relu) {
+                         int *out_copies, const KvPrefetch *pf, bool pdl, cudaStream_t s) {
   VB_CHECK_ARG(B >= 1 && B <= dg::TN, "gemm_decode_x: B=%d not in [1,64]", B);
   VB_CHECK_ARG(K % tc::BK == 0 && ldx % 4 == 0, "gemm_decode_x: K %% 64 != 0 or unaligned rows");
   const int tiles = (N + dg::TM - 1) / dg::TM;
   const int num_kb = K / tc::BK;
-  int splits = force_splits > 0 ? std::min(force_splits, std::min(kMaxForcedSplits, num_kb))
-                                : pick_splits(tiles, num_kb);
-  if (relu) splits = std::min(splits, 8);   // portable cluster size
+  const int splits = force_splits > 0 ? std::min(force_splits, std::min(kMaxForcedSplits, num_kb))
+                                      : pick_splits(tiles, num_kb);
   const int ldp = tiles * dg::TM;
-  if (!relu)
-    VB_CHECK_ARG(partials && stats && partial_bytes >= (size_t)splits * dg::TN * ldp * sizeof(float),
-                 "gemm_decode_x: partial buffer too small");
+  VB_CHECK_ARG(partials && stats && partial_bytes >= (size_t)splits * dg::TN * ldp * sizeof(float),
+               "gemm_decode_x: partial buffer too small");
   if (out_splits) *out_splits = splits;
   if (out_ldp) *out_ldp = ldp;
   if (out_copies) *out_copies = std::min(tiles, kLnFoldMaxCopies);
@@ -645,20 +555,13 @@ int launch_gemm_decode_x(const float *x, int B, int64_t ldx, const bf16 *Wf, int
   VB_TRY(tc::make_tmap(&tw, Wf, N, K, K, dg::TM));
   VB_TRY(tc::make_tmap_f32_dense(&tx, x, B, K, ldx, dg::TN, tc::BK));
   static PerDeviceOnce once;
-  if (once.first()) {
+  if (once.first())
     VB_CUDA(cudaFuncSetAttribute(dg::gemm_decode_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  dg::kSmemBytesX));
-    prefer_chain_carveout(dg::gemm_decode_x_kernel);
-  }
   KvPrefetch pf0{};
   if (pf) pf0 = *pf;
-  dg::XEpi xe{};
-  if (relu) {
-    xe.mode = 1; xe.N = N; xe.B = B; xe.d = K; xe.eps = relu->eps; xe.c = relu->c; xe.dvec = relu->dvec;
-    xe.out16 = relu->out16; xe.ld_out = relu->ld_out;
-  }
-  VB_CUDA(launch_kernel_cluster(dg::gemm_decode_x_kernel, dim3(tiles, splits), dim3(dg::kThreadsX), dg::kSmemBytesX, s,
-                                pdl, dim3(1, relu ? splits : 1, 1), tw, tx, num_kb, partials, ldp, stats, pf0, xe));
+  VB_CUDA(launch_kernel(dg::gemm_decode_x_kernel, dim3(tiles, splits), dim3(dg::kThreadsX), dg::kSmemBytesX, s, pdl,
+                        tw, tx, num_kb, partials, ldp, stats, pf0));
   count_launch();
   return VB_OK;
 }

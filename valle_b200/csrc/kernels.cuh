@@ -69,7 +69,6 @@ struct KvPrefetch {
   int B, H, cap, row_bytes;   // row_bytes = 64 * element size
   const int32_t *text_len, *prompt_len, *n_gen;
   int lo_pct, hi_pct;
-  int keep;   // mark the prefetched lines evict-last (they are read once, by the next attention launch)
 };
 // worker = one warp; `n_workers` warps of the grid share the streams.  Lane i of a warp fetches the lengths of the
 // warp's i-th stream up front (the three dependent global loads per stream would otherwise serialise the loop).
@@ -99,28 +98,7 @@ __device__ __forceinline__ void kv_prefetch(const KvPrefetch &pf, int worker, in
     const char *p = (const char *)((sidx & 1) ? pf.vbase : pf.kbase) + (int64_t)b * pf.seq_stride_bytes +
                     ((int64_t)h * pf.cap + r_lo) * pf.row_bytes;
     const int lines = ((r_hi - r_lo) * pf.row_bytes) >> 7;  // 128-byte lines
-    for (int l = lane; l < lines; l += 32) prefetch_l2(p + ((int64_t)l << 7), pf.keep);
-  }
-}
-
-// L2 prefetch of the weight matrices of the projections that FOLLOW an attention launch (out-proj, FFN1, FFN2, the next
-// layer's QKV: 25 MB per layer at d = 1024), issued by the attention CTAs ahead of their dependency wait.  The CTAs of
-// those projections cannot become resident -- and start their own weight TMA loads -- before the previous kernel's CTAs
-// leave the SMs (shared memory), so without this their weight fetch from HBM sits on the critical path of the chain
-// (FFN2: 7.2 us of block time); with it the loads hit L2.  The attention launch itself leaves HBM bandwidth unused
-// once 40 % of the KV streams are L2-resident.
-struct WPrefetch {
-  const void *ptr[4];
-  unsigned long long bytes[4];
-  int keep;   // mark the lines evict-last
-  int stream_evict_first;   // the attention's own K / V loads carry the evict-first policy
-};
-__device__ __forceinline__ void weight_prefetch(const WPrefetch &wp, unsigned gtid, unsigned n_threads) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (wp.ptr[i] == nullptr) continue;
-    const unsigned long long lines = wp.bytes[i] >> 7;
-    for (unsigned long long l = gtid; l < lines; l += n_threads) prefetch_l2((const char *)wp.ptr[i] + (l << 7), wp.keep);
+    for (int l = lane; l < lines; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + ((int64_t)l << 7)));
   }
 }
 
@@ -192,15 +170,9 @@ __device__ __forceinline__ void ln_fold_moments_finish(const LnFoldStats &f, flo
 __device__ __forceinline__ void ln_fold_moments(const LnFoldStats &f, int b, int which, float &mean, float &rstd) {
   ln_fold_moments_finish(f, ln_fold_moments_load(f, b, which), mean, rstd);
 }
-struct XRelu {           // finished rows of the folded projection: out16[b, n] = bf16(relu(LayerNorm(x) W^T + b))
-  const float *c, *dvec; // vb_ln_fold vectors
-  float eps;
-  bf16 *out16;
-  int64_t ld_out;
-};
 int launch_gemm_decode_x(const float *x, int B, int64_t ldx, const bf16 *Wf, int N, int K, int force_splits,
                          float *partials, size_t partial_bytes, float *stats, int *out_splits, int *out_ldp,
-                         int *out_copies, const KvPrefetch *pf, bool pdl, cudaStream_t s, const XRelu *relu = nullptr);
+                         int *out_copies, const KvPrefetch *pf, bool pdl, cudaStream_t s);
 int launch_ln_fold(const bf16 *W, int N, int K, const float *gamma, const float *beta, const float *bias, bf16 *wf,
                    float *c, float *dvec, cudaStream_t s);
 
@@ -225,7 +197,7 @@ int launch_attn_decode(const float *q, const float *qkv_part, int qkv_splits, in
                        int B, int n_head, int head_dim, void *kcache, void *vcache, int dtype,
                        int64_t cache_seq_stride, int cache_cap, const int32_t *text_len, const int32_t *prompt_len,
                        const int32_t *n_gen, const int32_t *finished, float *out, void *out16, void *workspace,
-                       bool pdl, cudaStream_t s, const LnFoldStats *fold = nullptr, const WPrefetch *wp = nullptr);
+                       bool pdl, cudaStream_t s, const LnFoldStats *fold = nullptr);
 
 // decode_fused.cu
 int launch_relu_reduce(const float *partials, int splits, int ldp, const float *bias, int B, int N, bf16 *out16,

@@ -150,8 +150,6 @@ int launch_ar_sample(float *logits, int64_t ld_logits, const float *partials, in
                      cudaStream_t s, const LnFoldStats *fold) {
   LnFoldStats f{};
   if (fold) f = *fold;
-  static PerDeviceOnce once;
-  if (once.first()) prefer_chain_carveout(ar_sample_kernel);
   const float *fold_d = fold ? head->fold.dvec : nullptr;
   VB_CUDA(launch_kernel(ar_sample_kernel, dim3(st->B), dim3(256), 0, s, pdl, logits, ld_logits, partials, splits, ldp,
                         head->n_vocab, head->eos_id, head->audio_emb, head->alpha, head->pe, head->pe_rows,
