@@ -543,8 +543,10 @@ int launch_gemm_decode_x(const float *x, int B, int64_t ldx, const bf16 *Wf, int
   VB_CHECK_ARG(K % tc::BK == 0 && ldx % 4 == 0, "gemm_decode_x: K %% 64 != 0 or unaligned rows");
   const int tiles = (N + dg::TM - 1) / dg::TM;
   const int num_kb = K / tc::BK;
-  const int splits = force_splits > 0 ? std::min(force_splits, std::min(kMaxForcedSplits, num_kb))
-                                      : pick_splits(tiles, num_kb);
+  int splits = force_splits > 0 ? std::min(force_splits, std::min(kMaxForcedSplits, num_kb)) : pick_splits(tiles, num_kb);
+  // keep a CTA's k-range inside the ring where the split cap allows it (wider models: more splits rather than a
+  // wrapping ring, whose later fp32 boxes would wait for the first MMAs)
+  splits = std::max(splits, std::min(kMaxForcedSplits, (num_kb + dg::kStagesX - 1) / dg::kStagesX));
   const int ldp = tiles * dg::TM;
   VB_CHECK_ARG(partials && stats && partial_bytes >= (size_t)splits * dg::TN * ldp * sizeof(float),
                "gemm_decode_x: partial buffer too small");
