@@ -279,7 +279,8 @@ gemm_decode_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
 // (sum x, sum x^2 over the k-range) ride along as two more partial sums per split.  The consumer of the partials
 // (attention prologue / ReLU reduce / sampler) applies rstd, mean, c and the folded bias -- the separate
 // residual + LayerNorm launch between two projections (transformer.py:296-302,57-74) disappears from the chain.
-constexpr int kStagesX = 4;   // the chain's split counts keep a CTA at <= 4 k-blocks: the ring never wraps
+constexpr int kStagesX = 4;   // the launcher picks the split count so that a CTA has <= 4 k-blocks where the split cap
+                              // allows (d_model <= 4096): every tile in flight at once; beyond that the ring wraps
 constexpr int kXfBytes = TN * BK * 4;  // 16 KB fp32 box
 constexpr int kStageBytesX = kWBytes + kXBytes + kXfBytes;  // 40 KB
 constexpr int kSmemBytesX = kStagesX * kStageBytesX + 1024 + 512;   // + alignment slack, barriers
